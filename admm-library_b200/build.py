@@ -1,0 +1,45 @@
+"""Builds libadmm_b200.so in-tree with nvcc for sm_100a (called by __graft_entry__.build())."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "admm_b200.cu")
+OUT_DIR = os.path.join(HERE, "lib")
+OUT = os.path.join(OUT_DIR, "libadmm_b200.so")
+
+NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-lineinfo", "-O3", "-std=c++17",
+              # explicit fma() only: the operation order written in the kernels is the one executed
+              "-fmad=false"]
+
+
+def sources() -> list[str]:
+    d = os.path.join(HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))] + \
+        [os.path.join(os.path.dirname(HERE), "include", "admm_b200.h")]
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(s) <= t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, SRC]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

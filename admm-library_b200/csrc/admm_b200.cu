@@ -1,0 +1,699 @@
+// admm_b200.cu -- host side of libadmm_b200.so: the C ABI of include/admm_b200.h, device memory
+// management, per-GPU shards and the launch loop of the persistent ADMM kernel.
+//
+// There is no reference implementation to mirror (/root/reference/README.md:1-2 is the whole of
+// the reference); the behaviour implemented here is the one written down in oracle/admm_ocp.m
+// (the MATLAB text BASELINE.json's north_star mandates) and SURVEY.md section 8(b).
+// No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <new>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/admm_b200.h"
+#include "host_util.cuh"
+#include "kernels.cuh"
+#include "dense.cuh"
+
+using namespace admmb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Shard;
+void dense_prepare(Shard &s, const admmb_opts *op);
+void dense_run(Shard &s, const admmb_opts *op);
+void dense_output(Shard &s, double *xo, double *zo, double *uo);
+void dense_tf32_xupdate(Shard &s);
+int dense_tf32_unit(Shard &s, int n, int64_t batch, size_t ld, const double *M, const double *S, const double *mc,
+                    const double *s0, const double *rt, double *x);
+
+// ------------------------------------------------------------------------------------------------
+// one GPU's share of a batch
+// ------------------------------------------------------------------------------------------------
+struct Shard {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = NUM_SMS_B200;
+    int64_t launches = 0;
+
+    // problem shape
+    int N = 0, nb = 0, n = 0, nsplitblk = 0, rows_zu = 0, nsplit = 0;
+    int64_t batch = 0, p_begin = 0;
+    size_t ld = 0;
+    bool dyn_batched = false, has_c = false, has_Q = false, has_R = false, has_q = false,
+         q_batched = false, par_batched = false, has_z0 = false, has_u0 = false, has_rho0 = false;
+    bool shared_factor = true, uploaded = false, ran = false;
+    bool use_dense = false;
+    int max_iter_alloc = 0;
+    bool hist_alloc = false;
+
+    std::vector<int> h_bdesc, h_rowmap;
+    DevBuf<double> rawA, rawB, rawc, rawQ, rawR, fac, s0, z, u, d, q, par, z0c, u0c, rho, rho0, usc, fin,
+        hist, xo, zo, uo, stage;
+    DevBuf<int> bdesc, rowmap, active0, active1, n_active, iters, status, fac_status, istage;
+    DevBuf<unsigned long long> counters;   // [0] refactor count, [1] converged, [2] sum iters, [3] max iters
+    DenseState dense;
+
+    void init(int dev)
+    {
+        device = dev;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+    }
+    void destroy()
+    {
+        cudaSetDevice(device);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    // host [cnt][R] -> device [R'][ld]
+    void upload_rows(const double *host, int64_t cnt, int R, double *dst, const int *d_rowmap)
+    {
+        stage.alloc((size_t)cnt * R);
+        CK(cudaMemcpyAsync(stage.p, host, sizeof(double) * (size_t)cnt * R, cudaMemcpyHostToDevice, stream));
+        dim3 grid((unsigned)((cnt + 31) / 32), (unsigned)((R + 31) / 32)), block(32, 8);
+        k_transpose_in<<<grid, block, 0, stream>>>(stage.p, cnt, R, dst, ld, d_rowmap);
+        ++launches;
+        CK(cudaGetLastError());
+    }
+    // device [R][ld] -> host [cnt][R]
+    template <typename T>
+    void download_rows(const T *src, int R, T *host, DevBuf<T> &stg)
+    {
+        stg.alloc((size_t)batch * R);
+        dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((R + 31) / 32)), block(32, 8);
+        k_transpose_out<T><<<grid, block, 0, stream>>>(src, ld, R, batch, stg.p);
+        ++launches;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host, stg.p, sizeof(T) * (size_t)batch * R, cudaMemcpyDeviceToHost, stream));
+    }
+
+    void upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt);
+    void run(const admmb_opts *op, admmb_result *res);
+    void download(admmb_result *res);
+    template <bool FSH, bool FSMEM>
+    void launch_iterate(const IterParams &P, bool adapt);
+    template <class K>
+    void launch_iterate_kernel(K kern, const IterParams &P, size_t smem);
+};
+
+void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt)
+{
+    CK(cudaSetDevice(device));
+    uploaded = false;
+    ran = false;
+    N = pb->N;
+    nb = 3 * N + 2;
+    n = 9 * N + 6;
+    batch = cnt;
+    p_begin = begin;
+    ld = round_up((size_t)cnt, 32);
+    dyn_batched = pb->dyn_batched != 0;
+    has_c = pb->c != nullptr;
+    has_Q = pb->Q != nullptr;
+    has_R = pb->R != nullptr;
+    has_q = pb->q != nullptr;
+    q_batched = has_q && pb->q_batched;
+    par_batched = pb->par_batched != 0;
+    has_z0 = pb->z0 != nullptr;
+    has_u0 = pb->u0 != nullptr;
+    has_rho0 = pb->rho0 != nullptr;
+
+    // block descriptors: type | compact slot << 8
+    h_bdesc.assign(nb, 0);
+    h_rowmap.assign(n, -1);
+    nsplitblk = 0;
+    for (int b = 0; b < nb; ++b) {
+        int t = pb->block_type[b];
+        if (t != BLK_NONE) {
+            for (int e = 0; e < 3; ++e) h_rowmap[3 * b + e] = 3 * nsplitblk + e;
+            h_bdesc[b] = t | (nsplitblk << 8);
+            ++nsplitblk;
+        } else {
+            h_bdesc[b] = t;
+        }
+    }
+    rows_zu = 3 * nsplitblk;
+    nsplit = rows_zu;
+    bdesc.alloc(nb);
+    rowmap.alloc(n);
+    CK(cudaMemcpyAsync(bdesc.p, h_bdesc.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(rowmap.p, h_rowmap.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+
+    const bool has_P = has_Q || has_R;
+    const bool per_rho = op->adapt_rho || has_rho0;
+    shared_factor = !dyn_batched && (!has_P || !per_rho);
+    use_dense = (op->xupdate == ADMMB_XUPDATE_DENSE);
+
+    // raw model
+    const size_t md = dyn_batched ? ld : 1;
+    auto up_model = [&](DevBuf<double> &buf, const double *host, int R) {
+        if (!host) { buf.release(); return; }
+        buf.alloc((size_t)R * md);
+        if (dyn_batched) upload_rows(host + (size_t)begin * R, cnt, R, buf.p, nullptr);
+        else CK(cudaMemcpyAsync(buf.p, host, sizeof(double) * R, cudaMemcpyHostToDevice, stream));
+    };
+    up_model(rawA, pb->A, 36 * N);
+    up_model(rawB, pb->B, 18 * N);
+    up_model(rawc, pb->c, 6 * N);
+    up_model(rawQ, pb->Q, 36 * (N + 1));
+    up_model(rawR, pb->R, 9 * N);
+
+    s0.alloc(6 * ld);
+    upload_rows(pb->s0 + (size_t)begin * 6, cnt, 6, s0.p, nullptr);
+    if (has_q) {
+        if (q_batched) { q.alloc((size_t)n * ld); upload_rows(pb->q + (size_t)begin * n, cnt, n, q.p, nullptr); }
+        else { q.alloc(n); CK(cudaMemcpyAsync(q.p, pb->q, sizeof(double) * n, cudaMemcpyHostToDevice, stream)); }
+    }
+    if (par_batched) {
+        par.alloc((size_t)8 * nb * ld);
+        upload_rows(pb->block_par + (size_t)begin * 8 * nb, cnt, 8 * nb, par.p, nullptr);
+    } else {
+        par.alloc((size_t)8 * nb);
+        CK(cudaMemcpyAsync(par.p, pb->block_par, sizeof(double) * 8 * nb, cudaMemcpyHostToDevice, stream));
+    }
+    if (has_z0) { z0c.alloc((size_t)rows_zu * ld); upload_rows(pb->z0 + (size_t)begin * n, cnt, n, z0c.p, rowmap.p); }
+    if (has_u0) { u0c.alloc((size_t)rows_zu * ld); upload_rows(pb->u0 + (size_t)begin * n, cnt, n, u0c.p, rowmap.p); }
+    if (has_rho0) {
+        rho0.alloc(ld);
+        CK(cudaMemcpyAsync(rho0.p, pb->rho0 + begin, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream));
+    }
+
+    fac.alloc(shared_factor ? (size_t)FS * N : (size_t)FS * N * ld);
+    z.alloc((size_t)rows_zu * ld);
+    u.alloc((size_t)rows_zu * ld);
+    d.alloc((size_t)3 * N * ld);
+    rho.alloc(ld);
+    usc.alloc(ld);
+    fin.alloc(4 * ld);
+    iters.alloc(ld);
+    status.alloc(ld);
+    fac_status.alloc(ld);
+    active0.alloc(ld);
+    active1.alloc(ld);
+    n_active.alloc(1);
+    counters.alloc(4);
+    CK(cudaMemsetAsync(fac_status.p, 0, sizeof(int) * ld, stream));
+    CK(cudaMemsetAsync(d.p, 0, sizeof(double) * 3 * N * ld, stream));
+    CK(cudaMemsetAsync(fin.p, 0, sizeof(double) * 4 * ld, stream));
+    if (op->history) {
+        const size_t need = (size_t)5 * op->max_iter * ld;
+        if (need * sizeof(double) > ((size_t)64 << 30)) throw CudaFail{cudaErrorMemoryAllocation, "history too large"};
+        hist.alloc(need);
+    }
+    max_iter_alloc = op->max_iter;
+    hist_alloc = op->history != 0;
+    CK(cudaStreamSynchronize(stream));
+    uploaded = true;
+}
+
+template <class K>
+void Shard::launch_iterate_kernel(K kern, const IterParams &P, size_t smem)
+{
+    static thread_local const void *configured[64];
+    static thread_local int n_configured = 0;
+    bool seen = false;
+    for (int i = 0; i < n_configured; ++i) seen |= configured[i] == (const void *)kern;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!seen && n_configured < 64) configured[n_configured++] = (const void *)kern;
+    // smallest CTA that still puts every active problem on the machine in one wave; otherwise the
+    // CTA size with the largest resident capacity (grid sized in whole waves by the block scheduler)
+    int bestT = 128, best_cap = -1;
+    for (int T = 32; T <= 256; T += 32) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+        if (occ <= 0) continue;
+        long cap = (long)occ * num_sms * T;
+        if ((long)P.n_active <= cap) { bestT = T; best_cap = -2; break; }
+        if (cap > best_cap) { best_cap = (int)cap; bestT = T; }
+    }
+    int grid = (P.n_active + bestT - 1) / bestT;
+    kern<<<grid, bestT, smem, stream>>>(P);
+    ++launches;
+    CK(cudaGetLastError());
+}
+
+template <bool FSH, bool FSMEM>
+void Shard::launch_iterate(const IterParams &P, bool adapt)
+{
+    size_t smem = ((FSH && FSMEM) ? sizeof(double) * FS * N : 0) + (par_batched ? 0 : sizeof(double) * 8 * nb) +
+                  sizeof(int) * nb;
+    smem = round_up(smem, 16);
+#define DISPATCH(C, Q, A) launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A>, P, smem)
+    if (has_c) {
+        if (has_q) { if (adapt) DISPATCH(true, true, true); else DISPATCH(true, true, false); }
+        else { if (adapt) DISPATCH(true, false, true); else DISPATCH(true, false, false); }
+    } else {
+        if (has_q) { if (adapt) DISPATCH(false, true, true); else DISPATCH(false, true, false); }
+        else { if (adapt) DISPATCH(false, false, true); else DISPATCH(false, false, false); }
+    }
+#undef DISPATCH
+}
+
+__global__ void k_stats(int64_t batch, const int *iters, const int *status, unsigned long long *counters)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long conv = 0, it = 0;
+    if (p < batch) { conv = status[p] == ST_CONVERGED; it = (unsigned long long)iters[p]; }
+    unsigned long long mx = it;
+    for (int o = 16; o > 0; o >>= 1) {
+        conv += __shfl_xor_sync(0xffffffffu, conv, o);
+        it += __shfl_xor_sync(0xffffffffu, it, o);
+        unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counters + 1, conv);
+        atomicAdd(counters + 2, it);
+        atomicMax(counters + 3, mx);
+    }
+}
+
+void Shard::run(const admmb_opts *op, admmb_result *res)
+{
+    CK(cudaSetDevice(device));
+    const bool has_P = has_Q || has_R;
+    const bool adapt = op->adapt_rho != 0;
+    const unsigned gb = (unsigned)((batch + 127) / 128);
+    CK(cudaEventRecord(ev0, stream));
+    CK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 4, stream));
+    CK(cudaMemsetAsync(fac_status.p, 0, sizeof(int) * ld, stream));
+
+    // ---- factorisation (row a1), once per rho
+    if (shared_factor) {
+        k_riccati_factor<<<1, 32, 0, stream>>>(N, 1, 0, 0, rawA.p, rawB.p, rawc.p, rawQ.p, rawR.p, ld, nullptr,
+                                                op->rho, bdesc.p, fac.p, nullptr);
+    } else {
+        k_riccati_factor<<<gb, 128, 0, stream>>>(N, batch, dyn_batched ? 1 : 0, 1, rawA.p, rawB.p, rawc.p, rawQ.p,
+                                                 rawR.p, ld, has_rho0 ? rho0.p : nullptr, op->rho, bdesc.p, fac.p,
+                                                 fac_status.p);
+    }
+    ++launches;
+    CK(cudaGetLastError());
+    k_reset<<<gb, 128, 0, stream>>>(batch, ld, rows_zu, z.p, u.p, has_z0 ? z0c.p : nullptr,
+                                    has_u0 ? u0c.p : nullptr, rho.p, has_rho0 ? rho0.p : nullptr, op->rho, usc.p,
+                                    iters.p, status.p, fac_status.p);
+    ++launches;
+    CK(cudaGetLastError());
+
+    if (use_dense) {
+        dense_run(*this, op);
+    } else {
+        k_iota<<<gb, 128, 0, stream>>>(active0.p, (int)batch);
+        ++launches;
+        IterParams P;
+        memset(&P, 0, sizeof(P));
+        P.N = N; P.nb = nb; P.n = n; P.ld = ld;
+        P.fac = fac.p; P.fac_rw = fac.p;
+        P.rawA = rawA.p; P.rawB = rawB.p; P.rawc = rawc.p; P.rawQ = rawQ.p; P.rawR = rawR.p;
+        P.raw_batched = dyn_batched;
+        P.s0 = s0.p; P.z = z.p; P.u = u.p; P.d = d.p;
+        P.q = has_q ? q.p : nullptr; P.q_batched = q_batched;
+        P.bdesc = bdesc.p; P.par = par.p; P.par_batched = par_batched;
+        P.rho = rho.p; P.usc = usc.p; P.iters = iters.p; P.status = status.p; P.fin = fin.p;
+        P.hist = op->history ? hist.p : nullptr;
+        P.hist_stride = (size_t)op->max_iter * ld;
+        P.refac_count = counters.p;
+        P.alpha = op->alpha; P.oma = 1.0 - op->alpha; P.reltol = op->reltol;
+        P.sqrtn_abs = sqrt((double)nsplit) * op->abstol;
+        P.mu = op->adapt_mu; P.tau = op->adapt_tau; P.inv_tau = 1.0 / op->adapt_tau;
+        P.adapt = adapt; P.every = op->adapt_every > 0 ? op->adapt_every : 1; P.until = op->adapt_until;
+        P.max_iter = op->max_iter; P.has_P = has_P;
+        int chunk = op->chunk > 0 ? op->chunk : 50;
+        if (adapt && P.every < chunk && P.every > 0) chunk = (chunk / P.every) * P.every;   // keep launches aligned
+        if (chunk < 1) chunk = 1;
+        P.chunk = chunk;
+        const bool fsmem = shared_factor && sizeof(double) * FS * N + sizeof(double) * 8 * nb + 4 * nb <= 200 * 1024;
+
+        int *cur = active0.p, *nxt = active1.p;
+        int n_act = (int)batch;
+        int done_iters = 0;
+        while (n_act > 0 && done_iters < op->max_iter) {
+            P.active = cur;
+            P.n_active = n_act;
+            if (shared_factor) { if (fsmem) launch_iterate<true, true>(P, adapt); else launch_iterate<true, false>(P, adapt); }
+            else launch_iterate<false, false>(P, adapt);
+            done_iters += chunk;
+            CK(cudaMemsetAsync(n_active.p, 0, sizeof(int), stream));
+            k_compact<<<(n_act + 255) / 256, 256, 0, stream>>>(cur, n_act, status.p, nxt, n_active.p);
+            ++launches;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&n_act, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            std::swap(cur, nxt);
+        }
+    }
+    k_stats<<<gb, 128, 0, stream>>>(batch, iters.p, status.p, counters.p);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, stream));
+    unsigned long long hc[4];
+    CK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (res) {
+        res->stats[0] = (int64_t)hc[1];
+        res->stats[1] = (int64_t)hc[2];
+        res->stats[2] = (int64_t)hc[3];
+        res->stats[3] = (int64_t)hc[0];
+        res->device_ms = ms;
+    }
+    ran = true;
+}
+
+void Shard::download(admmb_result *res)
+{
+    CK(cudaSetDevice(device));
+    const size_t pb = (size_t)p_begin;
+    if (res->x || res->z || res->u) {
+        if (res->x) xo.alloc((size_t)n * ld);
+        if (res->z) zo.alloc((size_t)n * ld);
+        if (res->u) uo.alloc((size_t)n * ld);
+        const unsigned gb = (unsigned)((batch + 127) / 128);
+        if (use_dense) {
+            dense_output(*this, res->x ? xo.p : nullptr, res->z ? zo.p : nullptr, res->u ? uo.p : nullptr);
+        } else if (shared_factor) {
+            if (has_c) k_output<true, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, res->x ? xo.p : nullptr, res->z ? zo.p : nullptr, res->u ? uo.p : nullptr);
+            else k_output<true, false><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, res->x ? xo.p : nullptr, res->z ? zo.p : nullptr, res->u ? uo.p : nullptr);
+        } else {
+            if (has_c) k_output<false, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, res->x ? xo.p : nullptr, res->z ? zo.p : nullptr, res->u ? uo.p : nullptr);
+            else k_output<false, false><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, res->x ? xo.p : nullptr, res->z ? zo.p : nullptr, res->u ? uo.p : nullptr);
+        }
+        ++launches;
+        CK(cudaGetLastError());
+        // one staging buffer per output so the three D2H copies can be queued back to back
+        static_assert(sizeof(double) == 8, "");
+        if (res->x) { download_rows<double>(xo.p, n, res->x + pb * n, stage); CK(cudaStreamSynchronize(stream)); }
+        if (res->z) { download_rows<double>(zo.p, n, res->z + pb * n, stage); CK(cudaStreamSynchronize(stream)); }
+        if (res->u) { download_rows<double>(uo.p, n, res->u + pb * n, stage); CK(cudaStreamSynchronize(stream)); }
+    }
+    auto dl = [&](double *host, const double *dev) {
+        if (host) CK(cudaMemcpyAsync(host + pb, dev, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream));
+    };
+    if (res->iters) CK(cudaMemcpyAsync(res->iters + pb, iters.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream));
+    if (res->status) CK(cudaMemcpyAsync(res->status + pb, status.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream));
+    dl(res->r_norm, fin.p);
+    dl(res->s_norm, fin.p + ld);
+    dl(res->eps_pri, fin.p + 2 * ld);
+    dl(res->eps_dual, fin.p + 3 * ld);
+    dl(res->rho, rho.p);
+    CK(cudaStreamSynchronize(stream));
+    if (hist_alloc && res->hist_r) {
+        const size_t hs = (size_t)max_iter_alloc * ld;
+        double *outs[5] = {res->hist_r, res->hist_s, res->hist_eps_pri, res->hist_eps_dual, res->hist_rho};
+        for (int a = 0; a < 5; ++a) {
+            if (!outs[a]) continue;
+            download_rows<double>(hist.p + a * hs, max_iter_alloc, outs[a] + pb * max_iter_alloc, stage);
+            CK(cudaStreamSynchronize(stream));
+        }
+    }
+}
+
+}  // namespace
+
+#include "dense_tf32.cuh"
+#include "dense_impl.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+struct admmb_ctx {
+    std::vector<Shard> shards;
+    std::string err;
+    std::mutex mu;
+    bool uploaded = false;
+    int64_t batch = 0;
+    int max_iter = 0;
+};
+
+namespace {
+
+int fail(admmb_ctx *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+int cuda_code(cudaError_t e)
+{
+    if (e == cudaErrorMemoryAllocation) return ADMMB_E_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return ADMMB_E_NODEVICE;
+    return ADMMB_E_CUDA;
+}
+
+int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
+{
+    if (!pb || !op) return fail(h, ADMMB_E_BADARG, "null problem/opts");
+    if (pb->N < 1 || pb->N > 4096) return fail(h, ADMMB_E_BADARG, "N out of range");
+    if (pb->batch < 1 || pb->batch > (int64_t)1 << 30) return fail(h, ADMMB_E_BADARG, "batch out of range");
+    if (!pb->A || !pb->B || !pb->s0 || !pb->block_type || !pb->block_par)
+        return fail(h, ADMMB_E_BADARG, "A, B, s0, block_type and block_par are required");
+    const int nb = 3 * pb->N + 2;
+    int nsplit = 0;
+    for (int b = 0; b < nb; ++b) {
+        int t = pb->block_type[b];
+        if (t < 0 || t > ADMMB_BLK_NONE) return fail(h, ADMMB_E_BADARG, "block_type[%d] = %d is not an ADMMB_BLK_* code", b, t);
+        nsplit += t != ADMMB_BLK_NONE;
+    }
+    if (nsplit == 0) return fail(h, ADMMB_E_BADARG, "no split block: nothing for ADMM to do");
+    for (int k = 0; k < pb->N; ++k)
+        if (pb->block_type[3 * k + 2] == ADMMB_BLK_NONE && !pb->R)
+            return fail(h, ADMMB_E_BADARG, "control block %d is unsplit and R is absent: x-update is singular", k);
+    if (!(op->rho > 0.0) || !std::isfinite(op->rho)) return fail(h, ADMMB_E_BADARG, "rho must be > 0");
+    if (!(op->alpha > 0.0 && op->alpha < 2.0)) return fail(h, ADMMB_E_BADARG, "alpha must be in (0,2)");
+    if (!(op->abstol >= 0.0) || !(op->reltol >= 0.0)) return fail(h, ADMMB_E_BADARG, "tolerances must be >= 0");
+    if (op->max_iter < 1) return fail(h, ADMMB_E_BADARG, "max_iter must be >= 1");
+    if (op->adapt_rho && (!(op->adapt_mu > 1.0) || !(op->adapt_tau > 1.0) || op->adapt_every < 1))
+        return fail(h, ADMMB_E_BADARG, "adaptive rho needs mu > 1, tau > 1, every >= 1");
+    if (op->xupdate < 0 || op->xupdate > 2) return fail(h, ADMMB_E_BADARG, "xupdate must be an ADMMB_XUPDATE_* code");
+    if (op->precision != ADMMB_PREC_FP64 && op->precision != ADMMB_PREC_TF32) return fail(h, ADMMB_E_BADARG, "bad precision");
+    if (op->precision == ADMMB_PREC_TF32 && op->xupdate != ADMMB_XUPDATE_DENSE)
+        return fail(h, ADMMB_E_BADARG, "TF32 applies to the dense x-update only");
+    if (op->xupdate == ADMMB_XUPDATE_DENSE) {
+        const bool has_P = pb->Q || pb->R;
+        if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
+        if (has_P && (op->adapt_rho || pb->rho0)) return fail(h, ADMMB_E_BADARG, "dense x-update with P != 0 needs one shared rho");
+        if (op->history) return fail(h, ADMMB_E_BADARG, "history is not recorded on the dense path");
+    }
+    return ADMMB_OK;
+}
+
+template <class Fn>
+int guarded(admmb_ctx *h, Fn fn)
+{
+    try {
+        return fn();
+    } catch (const CudaFail &f) {
+        return fail(h, cuda_code(f.e), "CUDA error %s (%s) at %s", cudaGetErrorName(f.e), cudaGetErrorString(f.e), f.what);
+    } catch (const std::bad_alloc &) {
+        return fail(h, ADMMB_E_NOMEM, "host allocation failed");
+    } catch (...) {
+        return fail(h, ADMMB_E_CUDA, "unexpected exception");
+    }
+}
+
+// run fn(shard_index) on every shard, one host thread per GPU when there are several
+template <class Fn>
+void for_each_shard(admmb_ctx *h, Fn fn)
+{
+    const int G = (int)h->shards.size();
+    if (G == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    std::vector<CudaFail> errs(G, CudaFail{cudaSuccess, ""});
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            try { fn(g); } catch (const CudaFail &f) { errs[g] = f; } catch (...) { errs[g] = CudaFail{cudaErrorUnknown, "worker"}; }
+        });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (errs[g].e != cudaSuccess) throw errs[g];
+}
+
+void shard_range(int64_t batch, int G, int g, int64_t &begin, int64_t &cnt)
+{
+    const int64_t per = (batch + G - 1) / G;
+    begin = std::min<int64_t>(batch, per * g);
+    cnt = std::min<int64_t>(batch, per * (g + 1)) - begin;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int admmb_version(void) { return ADMMB_VERSION; }
+
+int admmb_create(admmb_handle *out, const int *device_ids, int n_devices)
+{
+    if (!out) return fail(nullptr, ADMMB_E_BADARG, "null handle pointer");
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible <= 0)
+        return fail(nullptr, ADMMB_E_NODEVICE, "no usable CUDA device (%s); libadmm_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (n_devices <= 0) n_devices = device_ids ? 1 : visible;
+    admmb_ctx *h = new (std::nothrow) admmb_ctx();
+    if (!h) return fail(nullptr, ADMMB_E_NOMEM, "host allocation failed");
+    int rc = guarded(nullptr, [&]() {
+        h->shards.resize(n_devices);
+        for (int g = 0; g < n_devices; ++g) {
+            int dev = device_ids ? device_ids[g] : g;
+            if (dev < 0 || dev >= visible) { g_create_error = "device id out of range"; return (int)ADMMB_E_NODEVICE; }
+            h->shards[g].init(dev);
+        }
+        return (int)ADMMB_OK;
+    });
+    if (rc != ADMMB_OK) { delete h; return rc; }
+    *out = h;
+    return ADMMB_OK;
+}
+
+int admmb_destroy(admmb_handle h)
+{
+    if (!h) return ADMMB_E_BADARG;
+    for (auto &s : h->shards) {
+        cudaSetDevice(s.device);
+        cudaStreamSynchronize(s.stream);
+    }
+    for (auto &s : h->shards) s.destroy();
+    delete h;   // DevBuf destructors release the device memory (cudaFree is device-agnostic under UVA)
+    return ADMMB_OK;
+}
+
+const char *admmb_last_error(admmb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int admmb_device_count(admmb_handle h) { return h ? (int)h->shards.size() : 0; }
+
+int admmb_set_stream(admmb_handle h, void *cuda_stream)
+{
+    if (!h) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    Shard &s = h->shards[0];
+    s.stream = cuda_stream ? (cudaStream_t)cuda_stream : s.own_stream;
+    return ADMMB_OK;
+}
+
+int admmb_upload(admmb_handle h, const admmb_problem *pb, const admmb_opts *op)
+{
+    if (!h) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->uploaded = false;
+    int rc = validate(h, pb, op);
+    if (rc != ADMMB_OK) return rc;
+    const int G = (int)std::min<int64_t>((int64_t)h->shards.size(), pb->batch);
+    rc = guarded(h, [&]() {
+        for_each_shard(h, [&](int g) {
+            int64_t b, c;
+            shard_range(pb->batch, G, g, b, c);
+            Shard &s = h->shards[g];
+            if (g >= G || c <= 0) { s.uploaded = false; s.batch = 0; return; }
+            s.upload(pb, op, b, c);
+            if (s.use_dense) dense_prepare(s, op);
+        });
+        return (int)ADMMB_OK;
+    });
+    if (rc == ADMMB_OK) { h->uploaded = true; h->batch = pb->batch; h->max_iter = op->max_iter; }
+    return rc;
+}
+
+int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
+{
+    if (!h || !op) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->uploaded) return fail(h, ADMMB_E_STATE, "admmb_run called before a successful admmb_upload");
+    if (op->max_iter != h->max_iter && op->history) return fail(h, ADMMB_E_BADARG, "max_iter differs from the uploaded one while history is on");
+    std::vector<admmb_result> part(h->shards.size());
+    int rc = guarded(h, [&]() {
+        for_each_shard(h, [&](int g) {
+            Shard &s = h->shards[g];
+            memset(&part[g], 0, sizeof(admmb_result));
+            if (s.batch > 0 && s.uploaded) s.run(op, &part[g]);
+        });
+        return (int)ADMMB_OK;
+    });
+    if (rc != ADMMB_OK) return rc;
+    if (res) {
+        // the final statistics gather: 4 integers per GPU, summed (max for the third) on the host.
+        // In the one-process-per-GPU deployment (bench.py under torchrun) this is the NCCL all-reduce.
+        res->stats[0] = res->stats[1] = res->stats[2] = res->stats[3] = 0;
+        res->device_ms = 0.0;
+        res->launches = 0;
+        for (size_t g = 0; g < part.size(); ++g) {
+            res->stats[0] += part[g].stats[0];
+            res->stats[1] += part[g].stats[1];
+            res->stats[2] = std::max(res->stats[2], part[g].stats[2]);
+            res->stats[3] += part[g].stats[3];
+            res->device_ms = std::max(res->device_ms, part[g].device_ms);
+            res->launches += h->shards[g].launches;
+        }
+    }
+    return ADMMB_OK;
+}
+
+int admmb_download(admmb_handle h, admmb_result *res)
+{
+    if (!h || !res) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->uploaded) return fail(h, ADMMB_E_STATE, "admmb_download called before admmb_upload");
+    for (auto &s : h->shards)
+        if (s.batch > 0 && !s.ran) return fail(h, ADMMB_E_STATE, "admmb_download called before admmb_run");
+    return guarded(h, [&]() {
+        for_each_shard(h, [&](int g) {
+            Shard &s = h->shards[g];
+            if (s.batch > 0 && s.uploaded) s.download(res);
+        });
+        res->launches = 0;
+        for (auto &s : h->shards) res->launches += s.launches;
+        return (int)ADMMB_OK;
+    });
+}
+
+int admmb_solve(admmb_handle h, const admmb_problem *pb, const admmb_opts *op, admmb_result *res)
+{
+    if (!h || !res) return ADMMB_E_BADARG;
+    for (auto &s : h->shards) s.launches = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = admmb_upload(h, pb, op);
+    if (rc != ADMMB_OK) return rc;
+    auto t1 = std::chrono::steady_clock::now();
+    rc = admmb_run(h, op, res);
+    if (rc != ADMMB_OK) return rc;
+    auto t2 = std::chrono::steady_clock::now();
+    rc = admmb_download(h, res);
+    auto t3 = std::chrono::steady_clock::now();
+    res->h2d_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    res->d2h_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
+    return rc;
+}
+
+}  // extern "C"
+
+#include "unit_api.cuh"

@@ -1,0 +1,32 @@
+// common.cuh -- shared constants and small helpers of libadmm_b200 (device + host).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace admmb {
+
+// per-stage factor record, in doubles (mirrored by the oracle for tests only)
+//   K[3][6] Acl[6][6] Hinv[3][3] E[3][6] A[6][6] B[6][3] c[6] chat[6] pad[1]
+constexpr int F_K = 0, F_ACL = 18, F_HINV = 54, F_E = 63, F_A = 81, F_B = 117, F_C = 135,
+              F_CHAT = 141, FS = 148;
+
+constexpr int BLK_FREE = 0, BLK_L1 = 1, BLK_L1_BOX = 2, BLK_L2 = 3, BLK_L2_BALL = 4, BLK_BOX = 5,
+              BLK_BALL = 6, BLK_POINT = 7, BLK_NONE = 8;
+constexpr int PAR_LAM = 0, PAR_RAD = 1, PAR_LO = 2, PAR_HI = 5;
+constexpr int ST_CONVERGED = 0, ST_MAX_ITER = 1, ST_NAN = 2, ST_RUNNING = -1;
+
+constexpr int NUM_SMS_B200 = 148;
+
+// streaming loads/stores of the iterates: they are touched once per sweep, keep them out of L1
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double *p, double v)
+{
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+}  // namespace admmb

@@ -1,0 +1,105 @@
+// dense_impl.cuh -- host side of the dense shared-factor path (included by admm_b200.cu).
+#pragma once
+
+namespace {
+
+// Row a1': the dense factor is built ON DEVICE from the Riccati factor: column i of M is the
+// x-update of the unit right-hand side e_i with s_init = 0 and c = 0, i.e. one batch of n+6(+1)
+// "problems" pushed through the row-a2 kernel.
+void dense_build_factor(Shard &s, const double *fac_dev, bool has_c, double *M, double *S, double *mc)
+{
+    const int n = s.n, N = s.N;
+    const int64_t cols = n + 6 + 1;
+    const size_t ldc = round_up((size_t)cols, 32);
+    DevBuf<double> rt, s0, d, x;
+    rt.alloc((size_t)n * ldc);
+    s0.alloc(6 * ldc);
+    d.alloc((size_t)3 * N * ldc);
+    x.alloc((size_t)n * ldc);
+    CK(cudaMemsetAsync(rt.p, 0, sizeof(double) * n * ldc, s.stream));
+    CK(cudaMemsetAsync(s0.p, 0, sizeof(double) * 6 * ldc, s.stream));
+    k_dense_unit_rhs<<<(unsigned)((cols + 127) / 128), 128, 0, s.stream>>>(n, ldc, rt.p, s0.p);
+    ++s.launches;
+    // columns 0..n+5: homogeneous dynamics (c = 0); column n+6: rt = 0, s0 = 0, with c
+    k_xupdate_riccati<false><<<(unsigned)((n + 6 + 127) / 128), 128, 0, s.stream>>>(N, n + 6, ldc, fac_dev, s0.p, rt.p, d.p, x.p);
+    ++s.launches;
+    if (has_c) {
+        k_xupdate_riccati<true><<<1, 32, 0, s.stream>>>(N, 1, ldc, fac_dev, s0.p + (n + 6), rt.p + (n + 6), d.p + (n + 6), x.p + (n + 6));
+        ++s.launches;
+    }
+    CK(cudaGetLastError());
+    // x is [n rows][ldc cols]: row r, column i = M[r][i]  -> already row-major with leading dim ldc
+    k_dense_split_factor<<<(unsigned)((n + 127) / 128), 128, 0, s.stream>>>(n, ldc, x.p, has_c ? 1 : 0, M, S, mc);
+    ++s.launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s.stream));
+}
+
+void dense_prepare(Shard &s, const admmb_opts *)
+{
+    DenseState &D = s.dense;
+    D.M.alloc((size_t)s.n * s.n);
+    D.S.alloc((size_t)s.n * 6);
+    D.mc.alloc(s.n);
+    D.x.alloc((size_t)s.n * s.ld);
+    D.rt.alloc((size_t)s.n * s.ld);
+    D.running.alloc(1);
+    D.ready = false;
+}
+
+void dense_run(Shard &s, const admmb_opts *op)
+{
+    DenseState &D = s.dense;
+    const int n = s.n, nb = s.nb;
+    const unsigned gb = (unsigned)((s.batch + 127) / 128);
+    // factor (shared model, one rho): Riccati factor is already in s.fac
+    dense_build_factor(s, s.fac.p, s.has_c, D.M.p, D.S.p, D.mc.p);
+    D.ready = true;
+    CK(cudaMemsetAsync(D.x.p, 0, sizeof(double) * (size_t)n * s.ld, s.stream));
+    k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p,
+                                              s.has_q ? s.q.p : nullptr, s.q_batched, D.rt.p);
+    ++s.launches;
+    DenseStep ds;
+    ds.max_iter = op->max_iter;
+    ds.reltol = op->reltol;
+    ds.sqrtn_abs = sqrt((double)s.nsplit) * op->abstol;
+    ds.rho = s.rho.p; ds.iters = s.iters.p; ds.status = s.status.p; ds.fin = s.fin.p; ds.running = D.running.p;
+    const int chunk = op->chunk > 0 ? op->chunk : 25;
+    dim3 gg((unsigned)((s.batch + DG_BN - 1) / DG_BN), (unsigned)((n + DG_BM - 1) / DG_BM));
+    int running = 1;
+    for (int it = 1; it <= op->max_iter && running > 0; ++it) {
+        if (op->precision == ADMMB_PREC_TF32) {
+            dense_tf32_xupdate(s);
+        } else {
+            k_dense_xupdate_f64<<<gg, 256, 0, s.stream>>>(n, s.batch, s.ld, D.M.p, D.S.p, D.mc.p, s.s0.p, D.rt.p,
+                                                          s.status.p, D.x.p);
+            ++s.launches;
+        }
+        const bool check = (it % chunk) == 0 || it == op->max_iter;
+        if (check) CK(cudaMemsetAsync(D.running.p, 0, sizeof(int), s.stream));
+        ds.it = it;
+        k_prox_dual_residuals<true><<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched,
+                                                              nullptr, 0.0, op->alpha, D.x.p, s.z.p, s.u.p, nullptr,
+                                                              D.rt.p, s.has_q ? s.q.p : nullptr, s.q_batched, ds);
+        ++s.launches;
+        CK(cudaGetLastError());
+        if (check) {
+            CK(cudaMemcpyAsync(&running, D.running.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+        }
+    }
+}
+
+void dense_output(Shard &s, double *xo, double *zo, double *uo)
+{
+    DenseState &D = s.dense;
+    const unsigned gb = (unsigned)((s.batch + 127) / 128);
+    if (xo) CK(cudaMemcpyAsync(xo, D.x.p, sizeof(double) * (size_t)s.n * s.ld, cudaMemcpyDeviceToDevice, s.stream));
+    if (zo || uo) {
+        k_dense_output<<<gb, 128, 0, s.stream>>>(s.nb, s.batch, s.ld, s.bdesc.p, D.x.p, s.z.p, s.u.p, zo, uo);
+        ++s.launches;
+        CK(cudaGetLastError());
+    }
+}
+
+}  // namespace

@@ -1,0 +1,924 @@
+// kernels.cuh -- hand-written sm_100a kernels of the FP64 Riccati path.
+//
+// Data layout in HBM: batch-interleaved ("[row][ld]"): entry r of problem p lives at base[r*ld+p]
+// with ld = batch rounded up to 32.  One thread owns one problem, so a warp touches 32 consecutive
+// doubles (256 B) of one row per access -- fully coalesced -- and every per-problem reduction
+// (the five residual norms) is thread-local.  Shared-model data (the Riccati factor, the prox
+// parameter table) is staged in shared memory once per CTA and read by broadcast.
+//
+// Arithmetic: every operation is spelled out (mul/add/fma, fixed order) and the file is compiled
+// with -fmad=false, so results are bit-identical with the canonical-order oracle used by tests/
+// (SURVEY.md 7.3 H3).  Rows of SURVEY.md 8(a): a1 riccati_factor_dev / k_riccati_factor,
+// a2 backward_sweep + forward part of admm_iteration / k_xupdate_riccati, a3 prox_block_dev,
+// a4 process_block (relaxation, dual ascent, norms), a5 + a6 k_admm_iterate.
+#pragma once
+#include "common.cuh"
+
+namespace admmb {
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 Cholesky helpers (row a1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int chol3_dev(const double (&H)[3][3], double (&L)[6])
+{
+    double l00 = sqrt(H[0][0]);
+    double l10 = H[1][0] / l00;
+    double l20 = H[2][0] / l00;
+    double l11 = sqrt(fma(-l10, l10, H[1][1]));
+    double l21 = fma(-l20, l10, H[2][1]) / l11;
+    double l22 = sqrt(fma(-l21, l21, fma(-l20, l20, H[2][2])));
+    L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
+    return (l00 > 0.0 && l11 > 0.0 && l22 > 0.0) ? 0 : 1;
+}
+
+__device__ __forceinline__ void chol3_solve_dev(const double (&L)[6], double b0, double b1, double b2,
+                                                double &x0, double &x1, double &x2)
+{
+    double y0 = b0 / L[0];
+    double y1 = fma(-L[1], y0, b1) / L[2];
+    double y2 = fma(-L[4], y1, fma(-L[3], y0, b2)) / L[5];
+    x2 = y2 / L[5];
+    x1 = fma(-L[4], x2, y1) / L[2];
+    x0 = fma(-L[3], x2, fma(-L[1], x1, y0)) / L[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row a1: Riccati factor of ONE model.  Raw model rows are MATLAB column-major element indices;
+// element e of array X is at X[e*ldr] (pointer pre-offset by the problem index); factor entry
+// (k, off) is written to fac[(k*FS+off)*ldf].
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ int riccati_factor_dev(int N, const double *A, const double *B, const double *c,
+                                               const double *Q, const double *R, size_t ldr, double rho,
+                                               const int *bdesc, double *fac, size_t ldf)
+{
+    double P[6][6], Pk[6][6], T1[6][6], BtP[3][6], G1[3][6], H[3][3], L[6];
+    double Am[6][6], Bm[6][3], Km[3][6], Acl[6][6], cv[6];
+    const double rinv = 1.0 / rho;
+    int bad = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double w = (r == i && (bdesc[3 * N + r / 3] & 0xff) != BLK_NONE) ? 1.0 : 0.0;
+            if (Q) w = fma(Q[(size_t)(36 * N + r + 6 * i) * ldr], rinv, w);
+            P[r][i] = w;
+        }
+    for (int k = N - 1; k >= 0; --k) {
+        double *f = fac + (size_t)k * FS * ldf;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) Am[i][j] = A[(size_t)(36 * k + i + 6 * j) * ldr];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Bm[i][j] = B[(size_t)(18 * k + i + 6 * j) * ldr];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int l = 0; l < 6; ++l) {
+                double acc = Bm[0][j] * P[0][l];
+#pragma unroll
+                for (int i = 1; i < 6; ++i) acc = fma(Bm[i][j], P[i][l], acc);
+                BtP[j][l] = acc;
+            }
+        const double wc = ((bdesc[3 * k + 2] & 0xff) != BLK_NONE) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int m = 0; m <= j; ++m) {
+                double acc = (j == m) ? wc : 0.0;
+                if (R) acc = fma(R[(size_t)(9 * k + j + 3 * m) * ldr], rinv, acc);
+#pragma unroll
+                for (int l = 0; l < 6; ++l) acc = fma(BtP[j][l], Bm[l][m], acc);
+                H[j][m] = acc; H[m][j] = acc;
+            }
+        bad |= chol3_dev(H, L);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = BtP[j][0] * Am[0][i];
+#pragma unroll
+                for (int l = 1; l < 6; ++l) acc = fma(BtP[j][l], Am[l][i], acc);
+                G1[j][i] = acc;
+            }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double x0, x1, x2;
+            chol3_solve_dev(L, G1[0][i], G1[1][i], G1[2][i], x0, x1, x2);
+            Km[0][i] = -x0; Km[1][i] = -x1; Km[2][i] = -x2;
+            chol3_solve_dev(L, Bm[i][0], Bm[i][1], Bm[i][2], x0, x1, x2);
+            f[(size_t)(F_E + 0 * 6 + i) * ldf] = x0;
+            f[(size_t)(F_E + 1 * 6 + i) * ldf] = x1;
+            f[(size_t)(F_E + 2 * 6 + i) * ldf] = x2;
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            double x0, x1, x2;
+            chol3_solve_dev(L, m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0, x0, x1, x2);
+            f[(size_t)(F_HINV + 0 * 3 + m) * ldf] = x0;
+            f[(size_t)(F_HINV + 1 * 3 + m) * ldf] = x1;
+            f[(size_t)(F_HINV + 2 * 3 + m) * ldf] = x2;
+        }
+#pragma unroll
+        for (int l = 0; l < 6; ++l)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = Am[l][i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc = fma(Bm[l][j], Km[j][i], acc);
+                Acl[l][i] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) cv[r] = c ? c[(size_t)(6 * k + r) * ldr] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double acc = P[r][0] * cv[0];
+#pragma unroll
+            for (int l = 1; l < 6; ++l) acc = fma(P[r][l], cv[l], acc);
+            f[(size_t)(F_CHAT + r) * ldf] = acc;
+            f[(size_t)(F_C + r) * ldf] = cv[r];
+        }
+        f[(size_t)(FS - 1) * ldf] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) f[(size_t)(F_K + j * 6 + i) * ldf] = Km[j][i];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                f[(size_t)(F_ACL + l * 6 + i) * ldf] = Acl[l][i];
+                f[(size_t)(F_A + l * 6 + i) * ldf] = Am[l][i];
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) f[(size_t)(F_B + l * 3 + j) * ldf] = Bm[l][j];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = P[r][0] * Acl[0][i];
+#pragma unroll
+                for (int l = 1; l < 6; ++l) acc = fma(P[r][l], Acl[l][i], acc);
+                T1[r][i] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = (r == i && (bdesc[3 * k + r / 3] & 0xff) != BLK_NONE) ? 1.0 : 0.0;
+                if (Q) acc = fma(Q[(size_t)(36 * k + r + 6 * i) * ldr], rinv, acc);
+#pragma unroll
+                for (int l = 0; l < 6; ++l) acc = fma(Am[l][r], T1[l][i], acc);
+                Pk[r][i] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) P[r][i] = 0.5 * (Pk[r][i] + Pk[i][r]);
+    }
+    return bad;
+}
+
+// one thread per factor.  raw_batched: model p at column p of the raw arrays (stride ld), else one
+// contiguous shared model; fac_batched: factor written at column p (stride ld), else contiguous.
+__global__ void k_riccati_factor(int N, int64_t batch, int raw_batched, int fac_batched, const double *A,
+                                 const double *B, const double *c, const double *Q, const double *R, size_t ld,
+                                 const double *rho, double rho_shared, const int *bdesc, double *fac,
+                                 int *status)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const size_t ldr = raw_batched ? ld : 1, off = raw_batched ? (size_t)p : 0;
+    const size_t ldf = fac_batched ? ld : 1, offf = fac_batched ? (size_t)p : 0;
+    const double r = rho ? rho[p] : rho_shared;
+    int bad = riccati_factor_dev(N, A + off, B + off, c ? c + off : nullptr, Q ? Q + off : nullptr,
+                                 R ? R + off : nullptr, ldr, r, bdesc, fac + offf, ldf);
+    if (bad && status) status[p] = ST_NAN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row a3: prox of one 3-block.  par(slot) reads parameter `slot` of this block.
+// ------------------------------------------------------------------------------------------------
+template <class ParFn>
+__device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv, const double (&v)[3],
+                                               double (&z)[3])
+{
+    switch (type) {
+    case BLK_L1:
+    case BLK_L1_BOX: {
+        const double kap = par(PAR_LAM) * rinv;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            double t = v[e] > kap ? v[e] - kap : (v[e] < -kap ? v[e] + kap : 0.0);
+            if (type == BLK_L1_BOX) {
+                double lo = par(PAR_LO + e), hi = par(PAR_HI + e);
+                t = t < lo ? lo : (t > hi ? hi : t);
+            }
+            z[e] = t;
+        }
+        break;
+    }
+    case BLK_L2:
+    case BLK_L2_BALL: {
+        const double kap = par(PAR_LAM) * rinv;
+        double sq = v[0] * v[0];
+        sq = fma(v[1], v[1], sq);
+        sq = fma(v[2], v[2], sq);
+        double nrm = sqrt(sq);
+        if (nrm > kap) {
+            double mag = nrm - kap;
+            if (type == BLK_L2_BALL) { double rad = par(PAR_RAD); if (mag > rad) mag = rad; }
+            double sc = mag / nrm;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) z[e] = sc * v[e];
+        } else {
+            z[0] = 0.0; z[1] = 0.0; z[2] = 0.0;
+        }
+        break;
+    }
+    case BLK_BOX:
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            double lo = par(PAR_LO + e), hi = par(PAR_HI + e);
+            z[e] = v[e] < lo ? lo : (v[e] > hi ? hi : v[e]);
+        }
+        break;
+    case BLK_BALL: {
+        double c0 = par(PAR_LO), c1 = par(PAR_LO + 1), c2 = par(PAR_LO + 2), rad = par(PAR_RAD);
+        double w0 = v[0] - c0, w1 = v[1] - c1, w2 = v[2] - c2;
+        double sq = w0 * w0;
+        sq = fma(w1, w1, sq);
+        sq = fma(w2, w2, sq);
+        double nrm = sqrt(sq);
+        if (nrm > rad) {
+            double sc = rad / nrm;
+            z[0] = fma(sc, w0, c0); z[1] = fma(sc, w1, c1); z[2] = fma(sc, w2, c2);
+        } else {
+            z[0] = v[0]; z[1] = v[1]; z[2] = v[2];
+        }
+        break;
+    }
+    case BLK_POINT:
+        z[0] = par(PAR_LO); z[1] = par(PAR_LO + 1); z[2] = par(PAR_LO + 2);
+        break;
+    default:
+        z[0] = v[0]; z[1] = v[1]; z[2] = v[2];
+        break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters of the persistent multi-iteration kernel
+// ------------------------------------------------------------------------------------------------
+struct IterParams {
+    int N, nb, n;
+    int n_active;
+    const int *active;            // problem indices handled by this launch
+    size_t ld;
+    const double *fac;            // shared: [FS*N]; per problem: [FS*N][ld]
+    double *fac_rw;               // per-problem factor, writable (refactor)
+    const double *rawA, *rawB, *rawc, *rawQ, *rawR;   // raw model for the in-kernel refactor
+    int raw_batched;
+    const double *s0;             // [6][ld]
+    double *z, *u;                // [3*nsplitblk][ld] compact rows of the split blocks
+    double *d;                    // [3N][ld]: d_k after the backward sweep, a_k after the forward
+    const double *q;              // [n] or [n][ld]
+    int q_batched;
+    const int *bdesc;             // [nb]: type | slot << 8 (slot = compact index of a split block)
+    const double *par;            // [8*nb] or [8*nb][ld]
+    int par_batched;
+    double *rho, *usc;            // [ld] per-problem rho and pending dual scale
+    int *iters, *status;          // [ld]
+    double *fin;                  // [4][ld] r_norm, s_norm, eps_pri, eps_dual of the last iteration
+    double *hist;                 // 5 x [max_iter][ld] or nullptr
+    size_t hist_stride;
+    unsigned long long *refac_count;
+    double alpha, oma, reltol, sqrtn_abs, mu, tau, inv_tau;
+    int adapt, every, until, max_iter, chunk, has_P;
+};
+
+// factor accessor: shared (contiguous, smem or global) or per problem (interleaved, pre-offset by p)
+template <bool SHARED>
+struct FacRef {
+    const double *base;
+    size_t ld;
+    __device__ __forceinline__ double operator()(int k, int off) const
+    {
+        if (SHARED) return base[k * FS + off];
+        return base[((size_t)k * FS + off) * ld];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// One ADMM iteration of problem p (rows a2 + a3 + a4 fused): backward sweep, then a forward sweep
+// that turns each stage's x into z, u and the norm accumulators without x ever leaving registers.
+// ------------------------------------------------------------------------------------------------
+template <bool FSH, bool HAS_C, bool HAS_Q, bool ADAPT>
+__device__ __forceinline__ void admm_iteration(const IterParams &P, const size_t p, const FacRef<FSH> F,
+                                               const int *bdesc, const double *parS, const double rho,
+                                               const double sigma, double (&nr)[5])
+{
+    const int N = P.N;
+    const size_t ld = P.ld;
+    const double rinv = 1.0 / rho;
+    const double *zp = P.z + p, *up = P.u + p;
+    const double *qp = HAS_Q ? (P.q_batched ? P.q + p : P.q) : nullptr;
+    const size_t qld = P.q_batched ? ld : 1;
+
+    // right-hand side of block b: w*(z - u) - q/rho
+    auto load_rt = [&](int b, double (&t)[3]) {
+        const int de = bdesc[b];
+        if ((de & 0xff) != BLK_NONE) {
+            const size_t r0 = (size_t)(de >> 8) * 3;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                double zz = ld_stream(zp + (r0 + e) * ld);
+                double uu = ld_stream(up + (r0 + e) * ld);
+                if (ADAPT) uu = uu * sigma;
+                double v = zz - uu;
+                if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
+                t[e] = v;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) t[e] = HAS_Q ? -(qp[(size_t)(3 * b + e) * qld] * rinv) : 0.0;
+        }
+    };
+
+    // ---------------- backward sweep (row a2, first half)
+    double g[6];
+    {
+        double t0[3], t1[3];
+        load_rt(3 * N, t0);
+        load_rt(3 * N + 1, t1);
+        g[0] = t0[0]; g[1] = t0[1]; g[2] = t0[2]; g[3] = t1[0]; g[4] = t1[1]; g[5] = t1[2];
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        double rs[6], ra[3], pn[6];
+        {
+            double t0[3], t1[3];
+            load_rt(3 * k, t0);
+            load_rt(3 * k + 1, t1);
+            load_rt(3 * k + 2, ra);
+            rs[0] = t0[0]; rs[1] = t0[1]; rs[2] = t0[2]; rs[3] = t1[0]; rs[4] = t1[1]; rs[5] = t1[2];
+        }
+        if (HAS_C) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) g[i] = g[i] - F(k, F_CHAT + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = F(k, F_HINV + 3 * j + 0) * ra[0];
+            acc = fma(F(k, F_HINV + 3 * j + 1), ra[1], acc);
+            acc = fma(F(k, F_HINV + 3 * j + 2), ra[2], acc);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_E + 6 * j + i), g[i], acc);
+            st_stream(P.d + p + (size_t)(3 * k + j) * ld, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = rs[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_K + 6 * j + i), ra[j], acc);
+#pragma unroll
+            for (int l = 0; l < 6; ++l) acc = fma(F(k, F_ACL + 6 * l + i), g[l], acc);
+            pn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = pn[i];
+    }
+
+    // ---------------- forward sweep fused with prox / dual ascent / norms (rows a2, a3, a4)
+    double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
+    double *zw = P.z + p, *uw = P.u + p;
+    auto process_block = [&](int b, const double x0, const double x1, const double x2) {
+        const int de = bdesc[b];
+        const int type = de & 0xff;
+        if (type == BLK_NONE) return;
+        const size_t r0 = (size_t)(de >> 8) * 3;
+        const double xb[3] = {x0, x1, x2};
+        double zo[3], v[3], zn[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            zo[e] = ld_stream(zw + (r0 + e) * ld);
+            double uo = ld_stream(uw + (r0 + e) * ld);
+            if (ADAPT) uo = uo * sigma;
+            double xh = fma(P.alpha, xb[e], P.oma * zo[e]);
+            v[e] = xh + uo;
+        }
+        if (P.par_batched) {
+            const double *pp = P.par + p + (size_t)(8 * b) * ld;
+            prox_block_dev(type, [&](int s) { return pp[(size_t)s * ld]; }, rinv, v, zn);
+        } else {
+            const double *pp = parS + 8 * b;
+            prox_block_dev(type, [&](int s) { return pp[s]; }, rinv, v, zn);
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            double un = v[e] - zn[e];
+            double dr = xb[e] - zn[e];
+            double ds = zn[e] - zo[e];
+            rr = fma(dr, dr, rr);
+            ss = fma(ds, ds, ss);
+            xx = fma(xb[e], xb[e], xx);
+            zz = fma(zn[e], zn[e], zz);
+            uu = fma(un, un, uu);
+            st_stream(zw + (r0 + e) * ld, zn[e]);
+            st_stream(uw + (r0 + e) * ld, un);
+        }
+    };
+
+    double s[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = P.s0[p + (size_t)i * ld];
+    for (int k = 0; k < N; ++k) {
+        double a[3], sn[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = ld_stream(P.d + p + (size_t)(3 * k + j) * ld);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
+            a[j] = acc;
+            st_stream(P.d + p + (size_t)(3 * k + j) * ld, acc);
+        }
+        process_block(3 * k, s[0], s[1], s[2]);
+        process_block(3 * k + 1, s[3], s[4], s[5]);
+        process_block(3 * k + 2, a[0], a[1], a[2]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = F(k, F_A + 6 * i + 0) * s[0];
+#pragma unroll
+            for (int l = 1; l < 6; ++l) acc = fma(F(k, F_A + 6 * i + l), s[l], acc);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_B + 3 * i + j), a[j], acc);
+            if (HAS_C) acc = acc + F(k, F_C + i);
+            sn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = sn[i];
+    }
+    process_block(3 * N, s[0], s[1], s[2]);
+    process_block(3 * N + 1, s[3], s[4], s[5]);
+    nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rows a5 + a6: persistent multi-iteration launch.  Each thread runs up to `chunk` iterations of
+// its problem, evaluates the stopping test on device, leaves as soon as its problem is done
+// (per-problem early exit) and applies the residual-balancing rho update, refactorising only its
+// own problem when the factor depends on rho.
+// dynamic smem: [FSH ? FS*N : 0] factor, [par shared ? 8*nb : 0] parameters, [nb] block descriptors
+// ------------------------------------------------------------------------------------------------
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT>
+__global__ void __launch_bounds__(256) k_admm_iterate(const __grid_constant__ IterParams P)
+{
+    extern __shared__ double smem[];
+    double *facS = smem;
+    double *parS = facS + ((FSH && FSMEM) ? (size_t)FS * P.N : 0);
+    int *bdS = (int *)(parS + (P.par_batched ? 0 : 8 * P.nb));
+    if (FSH && FSMEM)
+        for (int i = threadIdx.x; i < FS * P.N; i += blockDim.x) facS[i] = P.fac[i];
+    if (!P.par_batched)
+        for (int i = threadIdx.x; i < 8 * P.nb; i += blockDim.x) parS[i] = P.par[i];
+    for (int i = threadIdx.x; i < P.nb; i += blockDim.x) bdS[i] = P.bdesc[i];
+    __syncthreads();
+
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_active) return;
+    const size_t p = (size_t)P.active[t];
+    if (P.status[p] != ST_RUNNING) return;
+
+    FacRef<FSH> F;
+    F.base = FSH ? (FSMEM ? facS : P.fac) : P.fac + p;
+    F.ld = P.ld;
+
+    double rho = P.rho[p];
+    double sigma = ADAPT ? P.usc[p] : 1.0;
+    int it = P.iters[p];
+    int st = ST_RUNNING;
+    double r_norm = 0.0, s_norm = 0.0, eps_pri = 0.0, eps_dual = 0.0;
+    for (int cnt = 0; cnt < P.chunk && st == ST_RUNNING; ++cnt) {
+        ++it;
+        double nr[5];
+        admm_iteration<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
+        sigma = 1.0;
+        r_norm = sqrt(nr[0]);
+        s_norm = rho * sqrt(nr[1]);
+        const double nx = sqrt(nr[2]), nz = sqrt(nr[3]);
+        eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
+        eps_dual = fma(P.reltol, rho * sqrt(nr[4]), P.sqrtn_abs);
+        if (P.hist) {
+            const size_t h = (size_t)(it - 1) * P.ld + p;
+            P.hist[h] = r_norm;
+            P.hist[h + P.hist_stride] = s_norm;
+            P.hist[h + 2 * P.hist_stride] = eps_pri;
+            P.hist[h + 3 * P.hist_stride] = eps_dual;
+            P.hist[h + 4 * P.hist_stride] = rho;
+        }
+        if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; break; }
+        if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; break; }
+        if (ADAPT && (it % P.every) == 0 && (P.until <= 0 || it <= P.until)) {
+            bool ch = false;
+            if (r_norm > P.mu * s_norm) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
+            else if (s_norm > P.mu * r_norm) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+            if (ch && !FSH && P.has_P) {
+                const size_t off = P.raw_batched ? p : 0, ldr = P.raw_batched ? P.ld : 1;
+                int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
+                                             P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
+                                             ldr, rho, bdS, P.fac_rw + p, P.ld);
+                atomicAdd(P.refac_count, 1ULL);
+                if (bad) { st = ST_NAN; break; }
+            }
+        }
+        if (it >= P.max_iter) { st = ST_MAX_ITER; break; }
+    }
+    P.iters[p] = it;
+    P.rho[p] = rho;
+    if (ADAPT) P.usc[p] = sigma;
+    P.status[p] = st;
+    P.fin[p] = r_norm;
+    P.fin[p + P.ld] = s_norm;
+    P.fin[p + 2 * P.ld] = eps_pri;
+    P.fin[p + 3 * P.ld] = eps_dual;
+}
+
+// ------------------------------------------------------------------------------------------------
+// active-list compaction between launches: keeps the problems still running, counts them.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_compact(const int *in, int n_in, const int *status, int *out, int *n_out)
+{
+    __shared__ int warp_cnt[32];
+    __shared__ int base;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int p = -1, keep = 0;
+    if (t < n_in) { p = in[t]; keep = status[p] == ST_RUNNING; }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+        base = tot ? atomicAdd(n_out, tot) : 0;
+    }
+    __syncthreads();
+    if (keep) out[base + warp_cnt[wid] + __popc(m & ((1u << lane) - 1))] = p;
+}
+
+__global__ void k_iota(int *a, int n)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state reset before a run: iterates from the warm start (or zero), counters, rho
+// ------------------------------------------------------------------------------------------------
+__global__ void k_reset(int64_t batch, size_t ld, int rows_zu, double *z, double *u, const double *z0,
+                        const double *u0, double *rho, const double *rho0, double rho_shared, double *usc,
+                        int *iters, int *status, const int *fac_status)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    for (int r = 0; r < rows_zu; ++r) {
+        z[(size_t)r * ld + p] = z0 ? z0[(size_t)r * ld + p] : 0.0;
+        u[(size_t)r * ld + p] = u0 ? u0[(size_t)r * ld + p] : 0.0;
+    }
+    rho[p] = rho0 ? rho0[p] : rho_shared;
+    usc[p] = 1.0;
+    iters[p] = 0;
+    status[p] = (fac_status && fac_status[p] == ST_NAN) ? ST_NAN : ST_RUNNING;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final outputs: x is re-propagated from the stored controls a_k (same operations as the forward
+// sweep => same bits), z/u are expanded from the compact split rows (BLK_NONE: z = x, u = 0).
+// Writes [n][ld] interleaved arrays; k_transpose_out turns them into [n x batch] column-major.
+// ------------------------------------------------------------------------------------------------
+template <bool FSH, bool HAS_C>
+__global__ void k_output(int N, int64_t batch, size_t ld, const double *fac, const double *s0,
+                         const double *d, const double *z, const double *u, const double *usc,
+                         const int *bdesc, const int *iters, double *xo, double *zo, double *uo)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    FacRef<FSH> F;
+    F.base = FSH ? fac : fac + p;
+    F.ld = ld;
+    const double sigma = usc ? usc[p] : 1.0;
+    const bool ran = iters[p] > 0;
+    auto emit = [&](int b, double x0, double x1, double x2) {
+        const int de = bdesc[b];
+        const double xb[3] = {x0, x1, x2};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t o = (size_t)(3 * b + e) * ld + p;
+            double zv = xb[e], uv = 0.0;
+            if ((de & 0xff) != BLK_NONE) {
+                const size_t r = ((size_t)(de >> 8) * 3 + e) * ld + p;
+                zv = z[r];
+                uv = u[r] * sigma;
+            }
+            if (xo) xo[o] = ran ? xb[e] : 0.0;
+            if (zo) zo[o] = ran ? zv : (((de & 0xff) != BLK_NONE) ? zv : 0.0);
+            if (uo) uo[o] = uv;
+        }
+    };
+    double s[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = s0[p + (size_t)i * ld];
+    for (int k = 0; k < N; ++k) {
+        double a[3], sn[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[j] = d[p + (size_t)(3 * k + j) * ld];
+        emit(3 * k, s[0], s[1], s[2]);
+        emit(3 * k + 1, s[3], s[4], s[5]);
+        emit(3 * k + 2, a[0], a[1], a[2]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = F(k, F_A + 6 * i + 0) * s[0];
+#pragma unroll
+            for (int l = 1; l < 6; ++l) acc = fma(F(k, F_A + 6 * i + l), s[l], acc);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_B + 3 * i + j), a[j], acc);
+            if (HAS_C) acc = acc + F(k, F_C + i);
+            sn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = sn[i];
+    }
+    emit(3 * N, s[0], s[1], s[2]);
+    emit(3 * N + 1, s[3], s[4], s[5]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout changes.  in: [batch][R] (each problem's R values contiguous, the MATLAB layout)
+//                  out: [R'][ld]   (row rowmap[r], or r when rowmap == nullptr; -1 rows dropped)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_transpose_in(const double *in, int64_t batch, int R, double *out, size_t ld,
+                               const int *rowmap)
+{
+    __shared__ double tile[32][33];
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int64_t p = p0 + i;
+        int r = r0 + threadIdx.x;
+        if (p < batch && r < R) tile[i][threadIdx.x] = in[(size_t)p * R + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i;
+        int64_t p = p0 + threadIdx.x;
+        if (p < batch && r < R) {
+            int ro = rowmap ? rowmap[r] : r;
+            if (ro >= 0) out[(size_t)ro * ld + p] = tile[threadIdx.x][i];
+        }
+    }
+}
+
+// in: [R][ld] interleaved  ->  out: [batch][R]
+template <typename T>
+__global__ void k_transpose_out(const T *in, size_t ld, int R, int64_t batch, T *out)
+{
+    __shared__ T tile[32][33];
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i;
+        int64_t p = p0 + threadIdx.x;
+        if (p < batch && r < R) tile[i][threadIdx.x] = in[(size_t)r * ld + p];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int64_t p = p0 + i;
+        int r = r0 + threadIdx.x;
+        if (p < batch && r < R) out[(size_t)p * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone kernels (unit entry points and the dense path)
+// ------------------------------------------------------------------------------------------------
+// Row a2 alone: x = Riccati x-update of rt, all arrays [rows][ld]; shared factor in global memory.
+template <bool HAS_C>
+__global__ void k_xupdate_riccati(int N, int64_t batch, size_t ld, const double *fac, const double *s0,
+                                  const double *rt, double *d, double *x)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    FacRef<true> F;
+    F.base = fac;
+    F.ld = ld;
+    double g[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = rt[(size_t)(9 * N + i) * ld + p];
+    for (int k = N - 1; k >= 0; --k) {
+        double rs[6], ra[3], pn[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rs[i] = rt[(size_t)(9 * k + i) * ld + p];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ra[j] = rt[(size_t)(9 * k + 6 + j) * ld + p];
+        if (HAS_C) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) g[i] = g[i] - F(k, F_CHAT + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = F(k, F_HINV + 3 * j + 0) * ra[0];
+            acc = fma(F(k, F_HINV + 3 * j + 1), ra[1], acc);
+            acc = fma(F(k, F_HINV + 3 * j + 2), ra[2], acc);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_E + 6 * j + i), g[i], acc);
+            d[(size_t)(3 * k + j) * ld + p] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = rs[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_K + 6 * j + i), ra[j], acc);
+#pragma unroll
+            for (int l = 0; l < 6; ++l) acc = fma(F(k, F_ACL + 6 * l + i), g[l], acc);
+            pn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = pn[i];
+    }
+    double s[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = s0[p + (size_t)i * ld];
+    for (int k = 0; k < N; ++k) {
+        double a[3], sn[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = d[(size_t)(3 * k + j) * ld + p];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
+            a[j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[(size_t)(9 * k + i) * ld + p] = s[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x[(size_t)(9 * k + 6 + j) * ld + p] = a[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = F(k, F_A + 6 * i + 0) * s[0];
+#pragma unroll
+            for (int l = 1; l < 6; ++l) acc = fma(F(k, F_A + 6 * i + l), s[l], acc);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_B + 3 * i + j), a[j], acc);
+            if (HAS_C) acc = acc + F(k, F_C + i);
+            sn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = sn[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[(size_t)(9 * N + i) * ld + p] = s[i];
+}
+
+// Rows a3 + a4 alone (the streaming prox / dual / residual kernel, "C4"): reads x, z, u once,
+// writes z, u once: 40 bytes per split entry.  All arrays are full-width [n][ld]; BLK_NONE rows are
+// skipped.  Optionally emits the next right-hand side rt = w*(z-u) - q/rho for the dense x-update
+// and, with SOLVE, evaluates the stopping test on device (per-problem early exit on the dense path).
+struct DenseStep {
+    int it;                    // iteration number of this step
+    int max_iter;
+    double reltol, sqrtn_abs;
+    const double *rho;         // [ld]
+    int *iters, *status;       // [ld]
+    double *fin;               // [4][ld]
+    int *running;              // incremented once per problem still running after this step
+};
+
+template <bool SOLVE>
+__global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const int *bdesc, const double *par,
+                                      int par_batched, const double *rinv_arr, double rinv_shared,
+                                      double alpha, const double *x, double *z, double *u, double *norms,
+                                      double *rt_next, const double *q, int q_batched, const DenseStep ds)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    if (SOLVE && ds.status[p] != ST_RUNNING) return;
+    const double rho = SOLVE ? ds.rho[p] : 0.0;
+    const double rinv = SOLVE ? 1.0 / rho : (rinv_arr ? rinv_arr[p] : rinv_shared);
+    const double oma = 1.0 - alpha;
+    double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        const int type = bdesc[b] & 0xff;
+        if (type == BLK_NONE) {
+            if (rt_next)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const size_t o = (size_t)(3 * b + e) * ld + p;
+                    rt_next[o] = q ? -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv) : 0.0;
+                }
+            continue;
+        }
+        double xb[3], zo[3], v[3], zn[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t o = (size_t)(3 * b + e) * ld + p;
+            xb[e] = ld_stream(x + o);
+            zo[e] = ld_stream(z + o);
+            double uo = ld_stream(u + o);
+            double xh = fma(alpha, xb[e], oma * zo[e]);
+            v[e] = xh + uo;
+        }
+        if (par_batched) {
+            const double *pp = par + p + (size_t)(8 * b) * ld;
+            prox_block_dev(type, [&](int s) { return pp[(size_t)s * ld]; }, rinv, v, zn);
+        } else {
+            const double *pp = par + 8 * b;
+            prox_block_dev(type, [&](int s) { return __ldg(pp + s); }, rinv, v, zn);
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t o = (size_t)(3 * b + e) * ld + p;
+            double un = v[e] - zn[e];
+            double dr = xb[e] - zn[e];
+            double dz = zn[e] - zo[e];
+            rr = fma(dr, dr, rr);
+            ss = fma(dz, dz, ss);
+            xx = fma(xb[e], xb[e], xx);
+            zz = fma(zn[e], zn[e], zz);
+            uu = fma(un, un, uu);
+            st_stream(z + o, zn[e]);
+            st_stream(u + o, un);
+            if (rt_next) {
+                double t = zn[e] - un;
+                if (q) t = fma(-q[q_batched ? o : (size_t)(3 * b + e)], rinv, t);
+                rt_next[o] = t;
+            }
+        }
+    }
+    if (norms) {
+        norms[p] = rr;
+        norms[ld + p] = ss;
+        norms[2 * ld + p] = xx;
+        norms[3 * ld + p] = zz;
+        norms[4 * ld + p] = uu;
+    }
+    if (SOLVE) {
+        const double r_norm = sqrt(rr), s_norm = rho * sqrt(ss);
+        const double nx = sqrt(xx), nz = sqrt(zz);
+        const double eps_pri = fma(ds.reltol, nx > nz ? nx : nz, ds.sqrtn_abs);
+        const double eps_dual = fma(ds.reltol, rho * sqrt(uu), ds.sqrtn_abs);
+        int st = ST_RUNNING;
+        if (!(isfinite(r_norm) && isfinite(s_norm))) st = ST_NAN;
+        else if (r_norm < eps_pri && s_norm < eps_dual) st = ST_CONVERGED;
+        else if (ds.it >= ds.max_iter) st = ST_MAX_ITER;
+        ds.iters[p] = ds.it;
+        ds.status[p] = st;
+        ds.fin[p] = r_norm;
+        ds.fin[p + ld] = s_norm;
+        ds.fin[p + 2 * ld] = eps_pri;
+        ds.fin[p + 3 * ld] = eps_dual;
+        if (st == ST_RUNNING) atomicAdd(ds.running, 1);
+    }
+}
+
+// first right-hand side of the dense path: rt = w*(z - u) - q/rho over full-width rows
+__global__ void k_dense_rt_init(int nb, int64_t batch, size_t ld, const int *bdesc, const double *z,
+                                const double *u, const double *rho, const double *q, int q_batched, double *rt)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const double rinv = 1.0 / rho[p];
+    for (int b = 0; b < nb; ++b) {
+        const bool split = (bdesc[b] & 0xff) != BLK_NONE;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t o = (size_t)(3 * b + e) * ld + p;
+            double t;
+            if (split) {
+                t = z[o] - u[o];
+                if (q) t = fma(-q[q_batched ? o : (size_t)(3 * b + e)], rinv, t);
+            } else {
+                t = q ? -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv) : 0.0;
+            }
+            rt[o] = t;
+        }
+    }
+}
+
+// dense-path outputs: z = x and u = 0 on BLK_NONE rows
+__global__ void k_dense_output(int nb, int64_t batch, size_t ld, const int *bdesc, const double *x,
+                               const double *z, const double *u, double *zo, double *uo)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    for (int b = 0; b < nb; ++b) {
+        const bool split = (bdesc[b] & 0xff) != BLK_NONE;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t o = (size_t)(3 * b + e) * ld + p;
+            if (zo) zo[o] = split ? z[o] : x[o];
+            if (uo) uo[o] = split ? u[o] : 0.0;
+        }
+    }
+}
+
+}  // namespace admmb

@@ -1,0 +1,245 @@
+"""Host-side mirror of the MATLAB surface  [x, z, u, hist] = admm_solve(prob, opts)
+(admm-library_b200/matlab/admm_solve.m) over the C ABI.
+
+Python arrays use the "math" layout of problems.py; this module converts them to the MATLAB
+column-major buffers the C ABI takes, calls libadmm_b200.so and returns NumPy arrays.  No numeric
+work happens here and there is no fallback: every call goes to the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
+PRECISION = {"fp64": 0, "tf32": 1}
+FS = 148  # doubles per stage in a factor record
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(L.c_dp)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(L.c_ip)
+
+
+def to_c_layout(prob: dict) -> dict:
+    """math-layout dict -> contiguous MATLAB column-major buffers + flags."""
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+    t = lambda a: None if a is None else np.ascontiguousarray(  # noqa: E731
+        np.swapaxes(np.asarray(a, dtype=np.float64), -1, -2))
+    Bsz = int(prob["s0"].shape[0])
+    Bd = int(prob["A"].shape[0])
+    if Bd not in (1, Bsz):
+        raise ValueError("A leading dimension must be 1 (shared) or batch")
+    for k in ("B", "c", "Q", "R"):
+        a = prob.get(k)
+        if a is not None and a.shape[0] != Bd:
+            raise ValueError(f"{k} must be batched like A")
+    m = dict(N=int(prob["A"].shape[1]), batch=Bsz, dyn_batched=int(Bd > 1),
+             A=t(prob["A"]), B=t(prob["B"]), c=f(prob.get("c")), Q=t(prob.get("Q")), R=t(prob.get("R")),
+             q=f(prob.get("q")), s0=f(prob["s0"]),
+             block_type=np.ascontiguousarray(prob["block_type"], dtype=np.int32),
+             block_par=f(prob["block_par"]), z0=f(prob.get("z0")), u0=f(prob.get("u0")),
+             rho0=f(prob.get("rho0")))
+    m["q_batched"] = int(m["q"] is not None and m["q"].shape[0] > 1)
+    m["par_batched"] = int(m["block_par"].shape[0] > 1)
+    return m
+
+
+def make_problem(m: dict) -> L.Problem:
+    return L.Problem(N=m["N"], batch=m["batch"], A=_dp(m["A"]), dyn_batched=m["dyn_batched"], B=_dp(m["B"]),
+                     c=_dp(m["c"]), Q=_dp(m["Q"]), R=_dp(m["R"]), q=_dp(m["q"]), q_batched=m["q_batched"],
+                     s0=_dp(m["s0"]), block_type=_ip(m["block_type"]), block_par=_dp(m["block_par"]),
+                     par_batched=m["par_batched"], z0=_dp(m["z0"]), u0=_dp(m["u0"]), rho0=_dp(m["rho0"]))
+
+
+def make_opts(opts: dict) -> L.Opts:
+    return L.Opts(rho=float(opts.get("rho", 1.0)), alpha=float(opts.get("alpha", 1.0)),
+                  abstol=float(opts.get("abstol", 1e-6)), reltol=float(opts.get("reltol", 1e-6)),
+                  max_iter=int(opts.get("max_iter", 1000)), adapt_rho=int(opts.get("adapt_rho", 0)),
+                  adapt_mu=float(opts.get("adapt_mu", 10.0)), adapt_tau=float(opts.get("adapt_tau", 2.0)),
+                  adapt_every=int(opts.get("adapt_every", 25)), adapt_until=int(opts.get("adapt_until", 0)),
+                  xupdate=XUPDATE[opts.get("xupdate", "auto")], precision=PRECISION[opts.get("precision", "fp64")],
+                  history=int(opts.get("history", 0)), chunk=int(opts.get("chunk", 0)))
+
+
+class ResultBuffers:
+    """Caller-owned output buffers (NumPy or any object exposing .ctypes / data pointers)."""
+
+    def __init__(self, batch: int, n: int, max_iter: int, history: bool, want=("x", "z", "u"), alloc=None):
+        alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype=dtype))
+        self.x = alloc((batch, n), np.float64) if "x" in want else None
+        self.z = alloc((batch, n), np.float64) if "z" in want else None
+        self.u = alloc((batch, n), np.float64) if "u" in want else None
+        self.iters = np.zeros(batch, dtype=np.int32)
+        self.status = np.zeros(batch, dtype=np.int32)
+        self.fin = {k: np.zeros(batch) for k in ("r_norm", "s_norm", "eps_pri", "eps_dual", "rho")}
+        self.hist = None
+        if history:
+            self.hist = {k: np.full((batch, max_iter), np.nan) for k in
+                         ("r_norm", "s_norm", "eps_pri", "eps_dual", "rho")}
+        self.c = L.Result(x=_dp(self.x), z=_dp(self.z), u=_dp(self.u), iters=_ip(self.iters),
+                          status=_ip(self.status), **{k: _dp(v) for k, v in self.fin.items()})
+        if history:
+            self.c.hist_r, self.c.hist_s = _dp(self.hist["r_norm"]), _dp(self.hist["s_norm"])
+            self.c.hist_eps_pri, self.c.hist_eps_dual = _dp(self.hist["eps_pri"]), _dp(self.hist["eps_dual"])
+            self.c.hist_rho = _dp(self.hist["rho"])
+
+    def hist_dict(self) -> dict:
+        out = dict(iters=self.iters, status=self.status, stats=list(self.c.stats),
+                   refactor_count=int(self.c.stats[3]), device_ms=self.c.device_ms, h2d_ms=self.c.h2d_ms,
+                   d2h_ms=self.c.d2h_ms, launches=int(self.c.launches), **self.fin)
+        if self.hist is not None:
+            # iterations a problem never ran stay NaN, as in the oracle
+            k = np.arange(self.hist["r_norm"].shape[1])[None, :]
+            mask = k >= self.iters[:, None]
+            for v in self.hist.values():
+                v[mask] = np.nan
+            out["hist"] = self.hist
+        return out
+
+
+class Solver:
+    """Owns an admmb_handle (device memory, streams, one worker thread per GPU)."""
+
+    def __init__(self, devices=None):
+        self._L = L.load()
+        self._h = C.c_void_p()
+        if devices is None:
+            ids, nd = None, 1
+        elif isinstance(devices, int):
+            ids, nd = None, devices
+        else:
+            ids, nd = (C.c_int * len(devices))(*devices), len(devices)
+        rc = self._L.admmb_create(C.byref(self._h), ids, nd)
+        if rc != L.OK:
+            msg = self._L.admmb_last_error(None)
+            raise L.AdmmError(rc, msg.decode() if msg else "")
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.admmb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != L.OK:
+            msg = self._L.admmb_last_error(self._h)
+            raise L.AdmmError(rc, msg.decode() if msg else "")
+
+    @property
+    def device_count(self) -> int:
+        return int(self._L.admmb_device_count(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._L.admmb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    # ---- one-shot -------------------------------------------------------------------------
+    def solve(self, prob: dict, opts: dict, want=("x", "z", "u")):
+        """[x, z, u, hist] = solve(prob, opts) -- host buffers in, host buffers out."""
+        m = to_c_layout(prob)
+        n = 9 * m["N"] + 6
+        op = make_opts(opts)
+        res = ResultBuffers(m["batch"], n, op.max_iter, bool(op.history), want)
+        pb = make_problem(m)
+        self._check(self._L.admmb_solve(self._h, C.byref(pb), C.byref(op), C.byref(res.c)))
+        return res.x, res.z, res.u, res.hist_dict()
+
+    # ---- staged ----------------------------------------------------------------------------
+    def upload(self, prob: dict, opts: dict):
+        m = to_c_layout(prob)
+        self._keep = m
+        self._n = 9 * m["N"] + 6
+        self._batch = m["batch"]
+        pb = make_problem(m)
+        op = make_opts(opts)
+        self._check(self._L.admmb_upload(self._h, C.byref(pb), C.byref(op)))
+
+    def upload_c(self, pb: L.Problem, op: L.Opts, batch: int, n: int):
+        """Upload from caller-built ctypes structs (e.g. pointing into pinned memory)."""
+        self._n, self._batch = n, batch
+        self._check(self._L.admmb_upload(self._h, C.byref(pb), C.byref(op)))
+
+    def run(self, opts: dict | L.Opts) -> dict:
+        op = opts if isinstance(opts, L.Opts) else make_opts(opts)
+        r = L.Result()
+        self._check(self._L.admmb_run(self._h, C.byref(op), C.byref(r)))
+        return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches))
+
+    def download(self, opts: dict, want=("x", "z", "u")):
+        op = make_opts(opts)
+        res = ResultBuffers(self._batch, self._n, op.max_iter, bool(op.history), want)
+        self._check(self._L.admmb_download(self._h, C.byref(res.c)))
+        return res.x, res.z, res.u, res.hist_dict()
+
+    def download_c(self, res: L.Result):
+        self._check(self._L.admmb_download(self._h, C.byref(res)))
+
+    # ---- unit kernels (tests) -----------------------------------------------------------------
+    def k_riccati_factor(self, prob: dict, rho: float) -> np.ndarray:
+        m = to_c_layout(prob)
+        assert m["dyn_batched"] == 0
+        fac = np.zeros((m["N"], FS))
+        self._check(self._L.admmb_k_riccati_factor(self._h, m["N"], _dp(m["A"]), _dp(m["B"]), _dp(m["c"]),
+                                                   _dp(m["Q"]), _dp(m["R"]), float(rho), _ip(m["block_type"]),
+                                                   _dp(fac)))
+        return fac
+
+    def k_xupdate_riccati(self, N: int, fac: np.ndarray, has_c: bool, s0: np.ndarray, rt: np.ndarray):
+        fac = np.ascontiguousarray(fac, dtype=np.float64)
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        rt = np.ascontiguousarray(rt, dtype=np.float64)
+        x = np.empty_like(rt)
+        self._check(self._L.admmb_k_xupdate_riccati(self._h, N, rt.shape[0], _dp(fac), int(has_c), _dp(s0),
+                                                    _dp(rt), _dp(x)))
+        return x
+
+    def k_prox_dual_residuals(self, N, block_type, block_par, rinv, alpha, x, z, u):
+        bt = np.ascontiguousarray(block_type, dtype=np.int32)
+        bp = np.ascontiguousarray(block_par, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        z = np.array(z, dtype=np.float64, order="C")
+        u = np.array(u, dtype=np.float64, order="C")
+        rinv = np.ascontiguousarray(rinv, dtype=np.float64)
+        norms = np.zeros((x.shape[0], 5))
+        self._check(self._L.admmb_k_prox_dual_residuals(self._h, N, x.shape[0], _ip(bt), _dp(bp),
+                                                        int(bp.shape[0] > 1), _dp(rinv), float(alpha), _dp(x),
+                                                        _dp(z), _dp(u), _dp(norms)))
+        return z, u, norms
+
+    def k_dense_factor(self, N: int, fac: np.ndarray, has_c: bool):
+        n = 9 * N + 6
+        fac = np.ascontiguousarray(fac, dtype=np.float64)
+        M, S, mc = np.zeros((n, n)), np.zeros((n, 6)), np.zeros(n)
+        self._check(self._L.admmb_k_dense_factor(self._h, N, _dp(fac), int(has_c), _dp(M), _dp(S), _dp(mc)))
+        return M, S, mc
+
+    def k_xupdate_dense(self, N, M, S, mc, s0, rt, precision="fp64"):
+        M, S, mc = (np.ascontiguousarray(a, dtype=np.float64) for a in (M, S, mc))
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        rt = np.ascontiguousarray(rt, dtype=np.float64)
+        x = np.empty_like(rt)
+        self._check(self._L.admmb_k_xupdate_dense(self._h, N, rt.shape[0], _dp(M), _dp(S), _dp(mc), _dp(s0),
+                                                  _dp(rt), PRECISION[precision], _dp(x)))
+        return x
+
+
+def admm_solve(prob: dict, opts: dict, devices=None):
+    """[x, z, u, hist] = admm_solve(prob, opts): same signature as oracle/admm_ocp.m."""
+    with Solver(devices) as s:
+        return s.solve(prob, opts)
