@@ -40,7 +40,8 @@ class Result(C.Structure):
                 ("r_norm", c_dp), ("s_norm", c_dp), ("eps_pri", c_dp), ("eps_dual", c_dp), ("rho", c_dp),
                 ("hist_r", c_dp), ("hist_s", c_dp), ("hist_eps_pri", c_dp), ("hist_eps_dual", c_dp),
                 ("hist_rho", c_dp), ("stats", C.c_int64 * 4), ("device_ms", C.c_double),
-                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("launches", C.c_int64)]
+                ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("launches", C.c_int64),
+                ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64)]
 
 
 class AdmmError(RuntimeError):

@@ -45,6 +45,25 @@ struct Shard {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = NUM_SMS_B200;
     int64_t launches = 0;
+    std::vector<cudaEvent_t> kev;     // event pairs around the dominant kernel's launches
+    size_t kev_used = 0;
+    double kernel_ms = 0.0;
+    int64_t kernel_launches = 0;
+    void kernel_tic()
+    {
+        if (kev_used + 2 > kev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); kev.push_back(e); }
+        }
+        CK(cudaEventRecord(kev[kev_used], stream));
+    }
+    void kernel_toc() { CK(cudaEventRecord(kev[kev_used + 1], stream)); kev_used += 2; }
+    void kernel_collect()   // after a stream sync
+    {
+        kernel_ms = 0.0;
+        kernel_launches = (int64_t)(kev_used / 2);
+        for (size_t i = 0; i < kev_used; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, kev[i], kev[i + 1])); kernel_ms += ms; }
+        kev_used = 0;
+    }
 
     // problem shape
     int N = 0, nb = 0, n = 0, nsplitblk = 0, rows_zu = 0, nsplit = 0;
@@ -54,6 +73,7 @@ struct Shard {
          q_batched = false, par_batched = false, has_z0 = false, has_u0 = false, has_rho0 = false;
     bool shared_factor = true, uploaded = false, ran = false;
     bool use_dense = false;
+    bool fast_pattern = false;   // stage states unsplit, every control split: prefetching kernel variant
     int max_iter_alloc = 0;
     bool hist_alloc = false;
 
@@ -81,6 +101,8 @@ struct Shard {
         cudaSetDevice(device);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto e : kev) cudaEventDestroy(e);
+        kev.clear();
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 
@@ -153,6 +175,10 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     }
     rows_zu = 3 * nsplitblk;
     nsplit = rows_zu;
+    fast_pattern = true;
+    for (int k = 0; k < N; ++k)
+        fast_pattern = fast_pattern && pb->block_type[3 * k] == BLK_NONE && pb->block_type[3 * k + 1] == BLK_NONE &&
+                       pb->block_type[3 * k + 2] != BLK_NONE;
     bdesc.alloc(nb);
     rowmap.alloc(n);
     CK(cudaMemcpyAsync(bdesc.p, h_bdesc.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream));
@@ -257,7 +283,11 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
     size_t smem = ((FSH && FSMEM) ? sizeof(double) * FS * N : 0) + (par_batched ? 0 : sizeof(double) * 8 * nb) +
                   sizeof(int) * nb;
     smem = round_up(smem, 16);
-#define DISPATCH(C, Q, A) launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A>, P, smem)
+#define DISPATCH(C, Q, A)                                                                      \
+    do {                                                                                      \
+        if (fast_pattern) launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, true>, P, smem);  \
+        else launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, false>, P, smem);              \
+    } while (0)
     if (has_c) {
         if (has_q) { if (adapt) DISPATCH(true, true, true); else DISPATCH(true, true, false); }
         else { if (adapt) DISPATCH(true, false, true); else DISPATCH(true, false, false); }
@@ -349,8 +379,10 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         while (n_act > 0 && done_iters < op->max_iter) {
             P.active = cur;
             P.n_active = n_act;
+            kernel_tic();
             if (shared_factor) { if (fsmem) launch_iterate<true, true>(P, adapt); else launch_iterate<true, false>(P, adapt); }
             else launch_iterate<false, false>(P, adapt);
+            kernel_toc();
             done_iters += chunk;
             CK(cudaMemsetAsync(n_active.p, 0, sizeof(int), stream));
             k_compact<<<(n_act + 255) / 256, 256, 0, stream>>>(cur, n_act, status.p, nxt, n_active.p);
@@ -370,7 +402,10 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     CK(cudaStreamSynchronize(stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    kernel_collect();
     if (res) {
+        res->kernel_ms = kernel_ms;
+        res->kernel_launches = kernel_launches;
         res->stats[0] = (int64_t)hc[1];
         res->stats[1] = (int64_t)hc[2];
         res->stats[2] = (int64_t)hc[3];
@@ -646,7 +681,11 @@ int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
         res->stats[0] = res->stats[1] = res->stats[2] = res->stats[3] = 0;
         res->device_ms = 0.0;
         res->launches = 0;
+        res->kernel_ms = 0.0;
+        res->kernel_launches = 0;
         for (size_t g = 0; g < part.size(); ++g) {
+            res->kernel_ms = std::max(res->kernel_ms, part[g].kernel_ms);
+            res->kernel_launches += part[g].kernel_launches;
             res->stats[0] += part[g].stats[0];
             res->stats[1] += part[g].stats[1];
             res->stats[2] = std::max(res->stats[2], part[g].stats[2]);

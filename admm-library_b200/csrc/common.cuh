@@ -6,9 +6,12 @@
 namespace admmb {
 
 // per-stage factor record, in doubles (mirrored by the oracle for tests only)
-//   K[3][6] Acl[6][6] Hinv[3][3] E[3][6] A[6][6] B[6][3] c[6] chat[6] pad[1]
-constexpr int F_K = 0, F_ACL = 18, F_HINV = 54, F_E = 63, F_A = 81, F_B = 117, F_C = 135,
-              F_CHAT = 141, FS = 148;
+//   K[3][6] Acl[6][6] Hinv[3][4] E[3][6] A[6][6] B[6][4] c[6] chat[6]
+// every matrix row starts on a 16-byte boundary (Hinv and B rows are padded to 4 doubles) so that the
+// shared-memory copy can be read with 128-bit loads.
+constexpr int F_K = 0, F_ACL = 18, F_HINV = 54, F_E = 66, F_A = 84, F_B = 120, F_C = 144,
+              F_CHAT = 150, FS = 156;
+constexpr int HINV_LD = 4, B_LD = 4;
 
 constexpr int BLK_FREE = 0, BLK_L1 = 1, BLK_L1_BOX = 2, BLK_L2 = 3, BLK_L2_BALL = 4, BLK_BOX = 5,
               BLK_BALL = 6, BLK_POINT = 7, BLK_NONE = 8;

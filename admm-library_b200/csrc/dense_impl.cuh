@@ -68,6 +68,7 @@ void dense_run(Shard &s, const admmb_opts *op)
     dim3 gg((unsigned)((s.batch + DG_BN - 1) / DG_BN), (unsigned)((n + DG_BM - 1) / DG_BM));
     int running = 1;
     for (int it = 1; it <= op->max_iter && running > 0; ++it) {
+        s.kernel_tic();
         if (op->precision == ADMMB_PREC_TF32) {
             dense_tf32_xupdate(s);
         } else {
@@ -82,6 +83,7 @@ void dense_run(Shard &s, const admmb_opts *op)
                                                               nullptr, 0.0, op->alpha, D.x.p, s.z.p, s.u.p, nullptr,
                                                               D.rt.p, s.has_q ? s.q.p : nullptr, s.q_batched, ds);
         ++s.launches;
+        s.kernel_toc();
         CK(cudaGetLastError());
         if (check) {
             CK(cudaMemcpyAsync(&running, D.running.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));

@@ -14,7 +14,26 @@ from . import _lib as L
 
 XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
 PRECISION = {"fp64": 0, "tf32": 1}
-FS = 148  # doubles per stage in a factor record
+FS = 156  # doubles per stage in a factor record (csrc/common.cuh)
+# name -> (offset, rows, cols, row stride) inside one record
+FAC_LAYOUT = dict(K=(0, 3, 6, 6), Acl=(18, 6, 6, 6), Hinv=(54, 3, 3, 4), E=(66, 3, 6, 6), A=(84, 6, 6, 6),
+                  B=(120, 6, 3, 4), c=(144, 1, 6, 6), chat=(150, 1, 6, 6))
+
+
+def unpack_factor(fac, layout=FAC_LAYOUT):
+    """factor records [N, FS] -> dict of [N, rows, cols] arrays."""
+    out = {}
+    for name, (off, r, c, ldr) in layout.items():
+        out[name] = np.stack([fac[:, off + i * ldr: off + i * ldr + c] for i in range(r)], axis=1)
+    return out
+
+
+def pack_factor(parts, N, layout=FAC_LAYOUT, fs=FS):
+    fac = np.zeros((N, fs))
+    for name, (off, r, c, ldr) in layout.items():
+        for i in range(r):
+            fac[:, off + i * ldr: off + i * ldr + c] = parts[name][:, i, :]
+    return fac
 
 
 def _dp(a):
@@ -91,7 +110,8 @@ class ResultBuffers:
     def hist_dict(self) -> dict:
         out = dict(iters=self.iters, status=self.status, stats=list(self.c.stats),
                    refactor_count=int(self.c.stats[3]), device_ms=self.c.device_ms, h2d_ms=self.c.h2d_ms,
-                   d2h_ms=self.c.d2h_ms, launches=int(self.c.launches), **self.fin)
+                   d2h_ms=self.c.d2h_ms, launches=int(self.c.launches), kernel_ms=self.c.kernel_ms,
+                   kernel_launches=int(self.c.kernel_launches), **self.fin)
         if self.hist is not None:
             # iterations a problem never ran stay NaN, as in the oracle
             k = np.arange(self.hist["r_norm"].shape[1])[None, :]
@@ -179,7 +199,8 @@ class Solver:
         op = opts if isinstance(opts, L.Opts) else make_opts(opts)
         r = L.Result()
         self._check(self._L.admmb_run(self._h, C.byref(op), C.byref(r)))
-        return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches))
+        return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches),
+                    kernel_ms=r.kernel_ms, kernel_launches=int(r.kernel_launches))
 
     def download(self, opts: dict, want=("x", "z", "u")):
         op = make_opts(opts)

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched ADMM hot path (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+
+A "step" is one full solve (to tolerance 1e-6, per-problem early exit) of one synthetic batch.
+Default workload = the configuration the north_star quotes its target on: CW impulsive
+fuel-optimal rendezvous QPs, N = 50, 6 states, 3 controls, shared dynamics, 65,536 problems per
+GPU (weak scaling; `--workload cfg2` selects configs[1]'s 4,096 per GPU).
+
+value  = problem-iterations/s, whole job, inputs already resident in HBM (admmb_upload done),
+         timed with CUDA events on the launching stream, max over ranks.
+e2e    = the same metric through the one-shot C-ABI call admmb_solve with pinned HOST buffers:
+         H2D of the problem and D2H of x, z, u, iters, status inside the timed region.
+Under torchrun (N > 1) each rank owns one GPU and its own shard of independent problems; the only
+collective is the final NCCL all-reduce of four statistics (converged, sum/max iterations, refactors).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "problem-iterations/sec"
+UNIT = "problem-iterations/s"
+
+WORKLOADS = {
+    # name: (generator, per-GPU batch, N, description)
+    "target65k": ("cfg2", 65536, 50, "65,536 CW impulsive rendezvous QPs per GPU, N=50, 6 states, 3 controls, "
+                                     "shared dynamics, L1 fuel cost + dv box, terminal point (north_star target config)"),
+    "cfg2": ("cfg2", 4096, 50, "configs[1]: 4,096 CW rendezvous QPs per GPU, N=50, shared dynamics"),
+    "cfg3": ("cfg3", 8192, 100, "configs[2]: CW low-thrust transfers with SOC thrust bound, N=100, 8,192 per GPU"),
+    "cfg4": ("cfg4", 16384, 50, "configs[3]: 16,384 elliptic rendezvous with per-problem time-varying STMs"),
+    "cfg5": ("cfg5", 131072, 50, "configs[4]: Monte Carlo dispersion sweep, adaptive rho, 131,072 per GPU"),
+}
+
+
+def make_workload(P, name: str, batch: int, rank: int):
+    gen = WORKLOADS[name][0]
+    N = WORKLOADS[name][2]
+    seed = 1000 * (rank + 1) + {"cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[gen]
+    if gen == "cfg2":
+        return P.cfg2_cw_batch(batch, N, seed)
+    if gen == "cfg3":
+        return P.cfg3_lowthrust_soc(batch, N, seed)
+    if gen == "cfg4":
+        return P.cfg4_elliptic(batch, N, seed)
+    return P.cfg5_montecarlo(batch, N, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def nsplit_of(prob) -> int:
+    return 3 * int((np.asarray(prob["block_type"]) != 8).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(prob, opts, sample: int, threads: int = 0) -> dict:
+    """Oracle port (C, OpenMP over problems) timed on the box's host cores on the first `sample`
+    problems of the workload.  The only place bench.py executes oracle/."""
+    from oracle import cpu
+    cpu.build()
+    sub = dict(prob)
+    sub["s0"] = prob["s0"][:sample]
+    for k in ("A", "B", "c", "Q", "R", "q", "block_par"):
+        a = prob.get(k)
+        if a is not None and a.shape[0] > 1:
+            sub[k] = a[:sample]
+    x, z, u, h = cpu.solve(sub, opts, nthreads=threads)
+    cores = cpu.lib().ocp_num_threads() if threads <= 0 else threads
+    return {"value": float(h["stats"][1]) / max(h["seconds"], 1e-9), "unit": UNIT, "cores": int(cores),
+            "kind": "port", "seconds": h["seconds"], "problem_iterations": int(h["stats"][1]),
+            "converged": int(h["stats"][0]),
+            "sample": f"first {sample} problems of the workload solved to tolerance by oracle/admm_ocp_cpu.c "
+                      f"(gcc -O2 -fopenmp, {cores} threads)"}
+
+
+def run_reference_arm(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference tree has
+    no code (README + LICENSE), so this is the oracle port on all host threads (kind = "port")."""
+    if rank != 0:
+        return
+    pkg = graft.load_pkg()
+    name = args.workload
+    per_gpu = args.batch or WORKLOADS[name][1]
+    sample = min(per_gpu, args.cpu_sample)
+    prob, opts = make_workload(pkg.problems, name, sample, 0)
+    times, iters_total = [], 0
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(prob, opts, sample)
+        if i >= args.warmup:
+            times.append(base["seconds"])
+            iters_total += base["problem_iterations"]
+    T = sum(times)
+    val = iters_total / T
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[name][3], "name": name, "cpu_sample_problems": sample,
+                       "tolerance": 1e-6, "max_iter": opts["max_iter"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["cpu_baseline"]["value"] = val
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="target65k", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="problems in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = graft.load_pkg()
+    L = pkg._lib
+    name = args.workload
+    per_gpu = args.batch or WORKLOADS[name][1]
+    prob, opts = make_workload(pkg.problems, name, per_gpu, rank)
+    if args.chunk:
+        opts["chunk"] = args.chunk
+    N = int(prob["A"].shape[1])
+    n = 9 * N + 6
+    nsplit = nsplit_of(prob)
+
+    solver = pkg.Solver(devices=[local_rank])
+    stream = torch.cuda.current_stream()
+    solver.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    solver.upload(prob, opts)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+
+    def step():
+        flush_buf.fill_(1)                       # L2 flush between steps (outside the timed events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r = solver.run(opts)
+        e1.record(stream)
+        return e0, e1, r
+
+    l_before = 0
+    for _ in range(args.warmup):
+        l_before = step()[2]["launches"]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    evs = []
+    for _ in range(args.steps):
+        evs.append(step())
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, e1, _ in evs]
+    dev_ms = float(sum(step_ms))
+    iters_rank = sum(r["stats"][1] for _, _, r in evs)
+    kernel_ms = sum(r["kernel_ms"] for _, _, r in evs)
+    kernel_launches = sum(r["kernel_launches"] for _, _, r in evs)
+    last = evs[-1][2]
+    # kernels launched inside the timed region: the library's counter is cumulative, the warm-up
+    # steps ended at l_before
+    gpu_launches = int(last["launches"] - l_before)
+    stats = torch.tensor([last["stats"][0], iters_rank, last["stats"][2], last["stats"][3]],
+                         dtype=torch.int64, device="cuda")
+    tmax = torch.tensor([dev_ms, kernel_ms, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        # the ONLY inter-GPU traffic of the whole job: 4 int64 + 3 float64 per rank, NCCL over NVLink
+        mx = stats[2:3].clone()
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        stats[2] = mx[0]
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    stats = stats.tolist()
+    dev_ms_max, kernel_ms_max, wall_ms_max = tmax.tolist()
+    total_iters = stats[1]
+    value = total_iters / (dev_ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_admm_iterate) ----------------------------------------
+    # algorithmic bytes per problem-iteration: read z,u + write z,u over the split entries (32 n)
+    alg_bytes_per_pi = 32.0 * nsplit
+    peak, peak_src = measured_peak_hbm()
+    achieved = (iters_rank * alg_bytes_per_pi) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_admm_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_problem_iteration": alg_bytes_per_pi,
+                "kernel_ms_per_step": kernel_ms / max(args.steps, 1),
+                "kernel_launches_per_step": kernel_launches / max(args.steps, 1),
+                "kernel_share_of_step": kernel_ms / dev_ms if dev_ms > 0 else None}
+
+    # ---- end-to-end arm: admmb_solve with pinned host buffers ---------------------------------------
+    e2e = None
+    launches_e2e = 0
+    if not args.no_e2e:
+        m = pkg.solver.to_c_layout(prob)
+
+        def pin(a):
+            if a is None:
+                return None, None
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t, t.numpy()
+
+        keep = {}
+        for k in ("A", "B", "c", "Q", "R", "q", "s0", "block_par", "z0", "u0", "rho0"):
+            keep[k] = pin(m[k])
+            m[k] = keep[k][1]
+        pb = pkg.solver.make_problem(m)
+        op = pkg.solver.make_opts(opts)
+
+        def pinned(shape, dtype):
+            t = torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
+            keep[id(t)] = t
+            return t.numpy()
+
+        res = pkg.solver.ResultBuffers(per_gpu, n, op.max_iter, False, ("x", "z", "u"), alloc=pinned)
+        h2d = sum(v[1].nbytes for k, v in keep.items() if isinstance(k, str) and v[1] is not None) + \
+            m["block_type"].nbytes
+        d2h = 3 * per_gpu * n * 8 + per_gpu * (2 * 4 + 5 * 8)
+
+        def e2e_step():
+            rc = L.load().admmb_solve(solver._h, C.byref(pb), C.byref(op), C.byref(res.c))
+            if rc != 0:
+                raise RuntimeError(L.load().admmb_last_error(solver._h))
+            return int(res.c.stats[1]), int(res.c.launches)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        it_e2e = 0
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            its, launches_e2e = e2e_step()
+            it_e2e += its
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        ii = torch.tensor([it_e2e], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        e2e = {"value": ii.item() / tt.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tt.item() / max(args.steps, 1),
+               "api": "admmb_solve (C ABI) with pinned host buffers; outputs x, z, u, iters, status, finals"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(prob, opts, min(per_gpu, args.cpu_sample))
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms_max / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": WORKLOADS[name][3], "name": name, "problems_per_gpu": per_gpu,
+                           "problems_total": per_gpu * world, "N": N, "n": n, "split_entries": nsplit,
+                           "tolerance": 1e-6, "max_iter": opts["max_iter"], "rho": opts["rho"],
+                           "alpha": opts["alpha"], "adapt_rho": opts["adapt_rho"],
+                           "l2": "flushed between steps (256 MB write, outside the timed events); "
+                                 "working set per GPU also exceeds L2 for >= 65,536 problems",
+                           "parallelism": f"batch shards, {world} x 1 GPU, no data-path collective"},
+                "time_to_tolerance_ms": dev_ms_max / max(args.steps, 1),
+                "converged": int(stats[0]), "problem_iterations_per_step": total_iters / max(args.steps, 1),
+                "max_iterations": int(stats[2]), "refactorisations": int(stats[3]),
+                "wall_ms_per_step_incl_flush": wall_ms_max / max(args.steps, 1),
+                "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    solver.close()
+
+
+if __name__ == "__main__":
+    main()

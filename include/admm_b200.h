@@ -113,6 +113,10 @@ typedef struct admmb_result {
     double device_ms;            /* device time of the solve phase (CUDA events, max over GPUs) */
     double h2d_ms, d2h_ms;       /* upload (+layout +factor) and download phases                */
     int64_t launches;            /* kernels launched by this library during the call            */
+    double kernel_ms;            /* summed device time of the dominant kernel's launches (the
+                                    persistent ADMM iteration kernel, or GEMM + prox on the dense
+                                    path), CUDA events on the launching stream, max over GPUs    */
+    int64_t kernel_launches;     /* how many launches kernel_ms covers                          */
 } admmb_result;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -138,7 +142,7 @@ int admmb_download(admmb_handle h, admmb_result *res);
 int admmb_set_stream(admmb_handle h, void *cuda_stream);
 
 /* ---- unit entry points: one kernel each, host buffers in / out (tests, SURVEY 4.2 tier T2) ---- */
-/* row a1: shared-model Riccati factor; fac_out [148 x N] records (layout in DESIGN.md)           */
+/* row a1: shared-model Riccati factor; fac_out [156 x N] records (layout in DESIGN.md)           */
 int admmb_k_riccati_factor(admmb_handle h, int32_t N, const double *A, const double *B, const double *c,
                            const double *Q, const double *R, double rho, const int32_t *block_type,
                            double *fac_out);
