@@ -3,6 +3,6 @@
 
 The directory name is not a valid Python identifier; import it through
 `__graft_entry__.load_pkg()` (registers it as `admm_library_b200`)."""
-from . import problems  # noqa: F401
+from . import dist, problems  # noqa: F401
 from ._lib import AdmmError, load  # noqa: F401
 from .solver import Solver, admm_solve  # noqa: F401

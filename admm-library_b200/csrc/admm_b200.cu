@@ -175,6 +175,11 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     }
     rows_zu = 3 * nsplitblk;
     nsplit = rows_zu;
+    use_dense = (op->xupdate == ADMMB_XUPDATE_DENSE);
+    if (use_dense) {   // the dense path keeps full-width iterates (BLK_NONE rows stay zero)
+        rows_zu = n;
+        for (int i = 0; i < n; ++i) h_rowmap[i] = i;
+    }
     fast_pattern = true;
     for (int k = 0; k < N; ++k)
         fast_pattern = fast_pattern && pb->block_type[3 * k] == BLK_NONE && pb->block_type[3 * k + 1] == BLK_NONE &&
@@ -187,7 +192,6 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     const bool has_P = has_Q || has_R;
     const bool per_rho = op->adapt_rho || has_rho0;
     shared_factor = !dyn_batched && (!has_P || !per_rho);
-    use_dense = (op->xupdate == ADMMB_XUPDATE_DENSE);
 
     // raw model
     const size_t md = dyn_batched ? ld : 1;

@@ -19,6 +19,7 @@ constexpr int PAR_LAM = 0, PAR_RAD = 1, PAR_LO = 2, PAR_HI = 5;
 constexpr int ST_CONVERGED = 0, ST_MAX_ITER = 1, ST_NAN = 2, ST_RUNNING = -1;
 
 constexpr int NUM_SMS_B200 = 148;
+constexpr double RHO_MAX = 1.0e6, RHO_MIN = 1.0e-6;   // adaptive rho never leaves this range
 
 // streaming loads/stores of the iterates: they are touched once per sweep, keep them out of L1
 __device__ __forceinline__ double ld_stream(const double *p)

@@ -778,8 +778,11 @@ __global__ void __launch_bounds__(256) k_admm_iterate(const __grid_constant__ It
         if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; break; }
         if (ADAPT && (it % P.every) == 0 && (P.until <= 0 || it <= P.until)) {
             bool ch = false;
-            if (r_norm > P.mu * s_norm) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
-            else if (s_norm > P.mu * r_norm) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+            if (r_norm > P.mu * s_norm) {
+                if (!(rho * P.tau > RHO_MAX)) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
+            } else if (s_norm > P.mu * r_norm) {
+                if (!(rho * P.inv_tau < RHO_MIN)) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+            }
             if (ch && !FSH && P.has_P) {
                 const size_t off = P.raw_batched ? p : 0, ldr = P.raw_batched ? P.ld : 1;
                 int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,

@@ -139,6 +139,7 @@ class Solver:
             msg = self._L.admmb_last_error(None)
             raise L.AdmmError(rc, msg.decode() if msg else "")
         self._keep = None
+        self._n = self._batch = 0
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -204,7 +205,7 @@ class Solver:
 
     def download(self, opts: dict, want=("x", "z", "u")):
         op = make_opts(opts)
-        res = ResultBuffers(self._batch, self._n, op.max_iter, bool(op.history), want)
+        res = ResultBuffers(max(self._batch, 1), max(self._n, 1), op.max_iter, bool(op.history), want)
         self._check(self._L.admmb_download(self._h, C.byref(res.c)))
         return res.x, res.z, res.u, res.hist_dict()
 

@@ -37,6 +37,7 @@ BLK_FREE, BLK_L1, BLK_L1_BOX, BLK_L2, BLK_L2_BALL, BLK_BOX, BLK_BALL, BLK_POINT,
 PAR_LAM, PAR_RAD, PAR_LO, PAR_HI = 0, 1, 2, 5
 
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NAN = 0, 1, 2
+RHO_MAX, RHO_MIN = 1.0e6, 1.0e-6      # adaptive rho never leaves this range
 
 
 # --------------------------------------------------------------------------- a1
@@ -245,8 +246,9 @@ def adapt_rho(r_norm, s_norm, rho, mu, tau):
     """Row a5.  Residual balancing (Boyd 2011 eq. 3.13).  Returns (rho_new, u_scale) with
     u_scale the factor the scaled dual must be multiplied by (rho_old / rho_new)."""
     inv_tau = 1.0 / tau
-    up = r_norm > mu * s_norm
-    dn = (~up) & (s_norm > mu * r_norm)
+    want_up = r_norm > mu * s_norm
+    up = want_up & ~(rho * tau > RHO_MAX)
+    dn = (~want_up) & (s_norm > mu * r_norm) & ~(rho * inv_tau < RHO_MIN)
     rho_new = np.where(up, rho * tau, np.where(dn, rho * inv_tau, rho))
     u_scale = np.where(up, inv_tau, np.where(dn, tau, 1.0))
     return rho_new, u_scale

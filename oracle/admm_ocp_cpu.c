@@ -387,11 +387,19 @@ static void prox_dual_residuals(int nb, const int32_t *bt, const double *par /* 
 }
 
 /* ------------------------------------------------------------------ a5: adapt_rho */
+#define RHO_MAX 1.0e6   /* rho is never pushed outside [RHO_MIN, RHO_MAX] (infeasible problems) */
+#define RHO_MIN 1.0e-6
 static int adapt_rho(double r_norm, double s_norm, double mu, double tau, double inv_tau,
                      double *rho, double *u_scale)
 {
-    if (r_norm > mu * s_norm) { *rho = *rho * tau; *u_scale = inv_tau; return 1; }
-    if (s_norm > mu * r_norm) { *rho = *rho * inv_tau; *u_scale = tau; return 1; }
+    if (r_norm > mu * s_norm) {
+        if (*rho * tau > RHO_MAX) return 0;
+        *rho = *rho * tau; *u_scale = inv_tau; return 1;
+    }
+    if (s_norm > mu * r_norm) {
+        if (*rho * inv_tau < RHO_MIN) return 0;
+        *rho = *rho * inv_tau; *u_scale = tau; return 1;
+    }
     return 0;
 }
 

@@ -1,0 +1,215 @@
+"""GPU unit tests (-m gpu; SURVEY.md 4.2 tier T2): each kernel alone, through its C-ABI entry point,
+against the same function of the canonical-order C oracle.  Bit-exact unless stated."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_identical
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+# the oracle's own factor-record layout (oracle/admm_ocp_cpu.c): name -> (offset, rows, cols, row stride)
+ORACLE_FAC = dict(K=(0, 3, 6, 6), Acl=(18, 6, 6, 6), Hinv=(54, 3, 3, 3), E=(63, 3, 6, 6), A=(81, 6, 6, 6),
+                  B=(117, 6, 3, 3), c=(135, 1, 6, 6), chat=(141, 1, 6, 6))
+
+
+def oracle_factor(cpu, pkg, prob, rho):
+    m = cpu.to_matlab_layout(prob)
+    N = m["N"]
+    fac = np.zeros((N, 148))
+    dp = lambda a: None if a is None else a.ctypes.data_as(cpu.c_dp)  # noqa: E731
+    L = cpu.lib()
+    L.ocp_riccati_factor.argtypes = [C.c_int, cpu.c_dp, cpu.c_dp, cpu.c_dp, cpu.c_dp, cpu.c_dp, C.c_double,
+                                     cpu.c_ip, cpu.c_dp]
+    L.ocp_riccati_factor(N, dp(m["A"]), dp(m["B"]), dp(m["c"]), dp(m["Q"]), dp(m["R"]), float(rho),
+                         m["block_type"].ctypes.data_as(cpu.c_ip), dp(fac))
+    return fac, pkg.solver.unpack_factor(fac, ORACLE_FAC)
+
+
+@pytest.mark.parametrize("case", ["cw", "lqr"])
+def test_riccati_factor_kernel(solver, cpu_oracle, pkg, P, case):
+    if case == "cw":
+        prob, _ = P.cfg2_cw_batch(batch=1, N=50)
+        rho = 1.0
+    else:
+        prob, _ = P.lqr_tracking(batch=1, N=30, seed=3)
+        rho = 0.37
+    got = pkg.solver.unpack_factor(solver.k_riccati_factor(prob, rho))
+    _, ref = oracle_factor(cpu_oracle, pkg, prob, rho)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), f"factor part {k} differs: {np.abs(got[k] - ref[k]).max():.3e}"
+
+
+@pytest.mark.parametrize("has_c", [False, True])
+def test_xupdate_riccati_kernel(solver, cpu_oracle, pkg, P, has_c):
+    prob, _ = P.lqr_tracking(batch=1, N=25, seed=4, with_affine=has_c)
+    N, n, B = 25, 9 * 25 + 6, 70
+    fac_o, parts = oracle_factor(cpu_oracle, pkg, prob, 0.8)
+    fac_g = pkg.solver.pack_factor(parts, N)
+    rng = np.random.default_rng(5)
+    s0, rt = rng.standard_normal((B, 6)), rng.standard_normal((B, n))
+    x = solver.k_xupdate_riccati(N, fac_g, has_c, s0, rt)
+    L = cpu_oracle.lib()
+    L.ocp_xupdate_riccati.argtypes = [C.c_int, cpu_oracle.c_dp, C.c_int, cpu_oracle.c_dp, cpu_oracle.c_dp, cpu_oracle.c_dp]
+    ref = np.zeros_like(rt)
+    for p in range(B):
+        xo = np.zeros(n)
+        L.ocp_xupdate_riccati(N, fac_o.ctypes.data_as(cpu_oracle.c_dp), int(has_c),
+                              np.ascontiguousarray(s0[p]).ctypes.data_as(cpu_oracle.c_dp),
+                              np.ascontiguousarray(rt[p]).ctypes.data_as(cpu_oracle.c_dp), xo.ctypes.data_as(cpu_oracle.c_dp))
+        ref[p] = xo
+    assert np.array_equal(x, ref)
+
+
+@pytest.mark.parametrize("par_batched", [False, True])
+def test_prox_dual_residual_kernel_all_block_types(solver, cpu_oracle, P, par_batched):
+    N, B = 10, 45
+    n, nb = 9 * N + 6, 3 * N + 2
+    rng = np.random.default_rng(6)
+    bt = (np.arange(nb) % 9).astype(np.int32)
+    bp = np.zeros((B if par_batched else 1, nb, 8))
+    bp[..., 0] = rng.uniform(0.05, 0.5, bp.shape[:2])
+    bp[..., 1] = rng.uniform(0.2, 1.0, bp.shape[:2])
+    bp[..., 2:5] = rng.uniform(-0.8, -0.1, bp.shape[:2] + (3,))
+    bp[..., 5:8] = rng.uniform(0.1, 0.8, bp.shape[:2] + (3,))
+    x, z, u = (rng.standard_normal((B, n)) for _ in range(3))
+    rinv = rng.uniform(0.5, 2.0, B)
+    zg, ug, ng = solver.k_prox_dual_residuals(N, bt, bp, rinv, 1.4, x, z, u)
+    L = cpu_oracle.lib()
+    dp = cpu_oracle.c_dp
+    L.ocp_prox_dual_residuals.argtypes = [C.c_int, cpu_oracle.c_ip, dp, C.c_double, C.c_double, dp, dp, dp, dp]
+    for p in range(B):
+        zo, uo, no = z[p].copy(), u[p].copy(), np.zeros(5)
+        par = np.ascontiguousarray(bp[p if par_batched else 0])
+        L.ocp_prox_dual_residuals(nb, bt.ctypes.data_as(cpu_oracle.c_ip), par.ctypes.data_as(dp), float(rinv[p]), 1.4,
+                                  np.ascontiguousarray(x[p]).ctypes.data_as(dp), zo.ctypes.data_as(dp),
+                                  uo.ctypes.data_as(dp), no.ctypes.data_as(dp))
+        split = np.repeat(bt != 8, 3)
+        assert np.array_equal(zg[p][split], zo[split]) and np.array_equal(ug[p][split], uo[split])
+        assert np.array_equal(zg[p][~split], z[p][~split])       # BLK_NONE rows untouched
+        assert np.array_equal(ng[p], no)
+
+
+def test_dense_factor_and_fp64_dense_xupdate_kernels(solver, cpu_oracle, pkg, P):
+    prob, _ = P.lqr_tracking(batch=1, N=12, seed=8)
+    N, n, B = 12, 9 * 12 + 6, 150
+    fac_o, parts = oracle_factor(cpu_oracle, pkg, prob, 1.3)
+    M, S, mc = solver.k_dense_factor(N, pkg.solver.pack_factor(parts, N), True)
+    L = cpu_oracle.lib()
+    dp = cpu_oracle.c_dp
+    Mo, So, mo = np.zeros((n, n)), np.zeros((n, 6)), np.zeros(n)
+    L.ocp_kkt_dense_factor.argtypes = [C.c_int, dp, C.c_int, dp, dp, dp]
+    L.ocp_kkt_dense_factor(N, fac_o.ctypes.data_as(dp), 1, Mo.ctypes.data_as(dp), So.ctypes.data_as(dp), mo.ctypes.data_as(dp))
+    assert np.array_equal(M, Mo) and np.array_equal(S, So) and np.array_equal(mc, mo)
+    # the dense factor really is KKT^-1 restricted (independent check against numpy.linalg)
+    from oracle import admm_ocp as O
+    wblk, _ = O.split_weights(prob["block_type"])
+    d = O.kkt_dense_factor(prob["A"][0], prob["B"][0], prob["c"][0], prob["Q"][0], prob["R"][0], 1.3, wblk)
+    assert np.allclose(M, d["M"], atol=1e-9) and np.allclose(S, d["S"], atol=1e-9) and np.allclose(mc, d["mc"], atol=1e-9)
+    rng = np.random.default_rng(9)
+    s0, rt = rng.standard_normal((B, 6)), rng.standard_normal((B, n))
+    x = solver.k_xupdate_dense(N, M, S, mc, s0, rt, "fp64")
+    L.ocp_xupdate_dense.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp]
+    for p in range(0, B, 7):
+        xo = np.zeros(n)
+        L.ocp_xupdate_dense(n, Mo.ctypes.data_as(dp), So.ctypes.data_as(dp), mo.ctypes.data_as(dp),
+                            np.ascontiguousarray(s0[p]).ctypes.data_as(dp), np.ascontiguousarray(rt[p]).ctypes.data_as(dp),
+                            xo.ctypes.data_as(dp))
+        assert np.array_equal(x[p], xo)
+
+
+@pytest.mark.parametrize("case", ["lqr", "cw"])
+def test_dense_fp64_path_end_to_end(solver, cpu_oracle, P, case):
+    if case == "lqr":
+        prob, opts = P.lqr_tracking(batch=70, N=10, seed=2)
+        opts = dict(opts, max_iter=120, xupdate="dense")
+    else:
+        prob, opts = P.cfg2_cw_batch(batch=130, N=12, seed=2)
+        opts = dict(opts, max_iter=250, xupdate="dense", alpha=1.5)
+    got = solver.solve(prob, opts)
+    ref = cpu_oracle.solve(prob, opts)
+    assert_bit_identical(got, ref, f"dense fp64 {case}")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
+def test_gpu_reproduces_golden_fixtures(solver, path):
+    """Committed NumPy-oracle vectors: same iteration counts, x/z/u within 1e-9 relative (north_star bar)."""
+    g = np.load(path)
+    prob = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    prob["N"] = prob["A"].shape[1]
+    opts = {k[4:]: g[k].item() for k in g.files if k.startswith("opt_")}
+    x, z, u, h = solver.solve(prob, opts)
+    assert np.array_equal(h["iters"], g["out_iters"])
+    assert np.array_equal(h["status"], g["out_status"])
+    for a, b in ((x, g["out_x"]), (z, g["out_z"]), (u, g["out_u"])):
+        scale = max(1.0, np.abs(b).max())
+        assert np.abs(a - b).max() <= 1e-9 * scale
+    assert np.allclose(h["hist"]["r_norm"], g["out_hist_r"], rtol=1e-7, atol=1e-12, equal_nan=True)
+    assert h["refactor_count"] == int(g["out_refactor"])
+
+
+def test_staged_api_and_repeatability(solver, cpu_oracle, P):
+    prob, opts = P.cfg2_cw_batch(batch=300, N=20, seed=8)
+    opts = dict(opts, max_iter=400)
+    solver.upload(prob, opts)
+    r1 = solver.run(opts)
+    a = solver.download(opts)
+    r2 = solver.run(opts)                       # run() restarts from the uploaded warm start
+    b = solver.download(opts)
+    assert r1["stats"] == r2["stats"] and r1["kernel_launches"] > 0
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    ref = cpu_oracle.solve(prob, opts)
+    assert_bit_identical(a, ref, "staged")
+    assert r1["stats"][:3] == [int(v) for v in ref[3]["stats"][:3]]
+    x_only = solver.download(opts, want=("x",))
+    assert x_only[1] is None and np.array_equal(x_only[0], a[0])
+
+
+def test_bad_arguments_are_refused_not_crashed(solver, pkg, P):
+    prob, opts = P.cfg2_cw_batch(batch=4, N=5, seed=1)
+    E = pkg._lib.E_BADARG
+    for bad in (dict(rho=-1.0), dict(alpha=2.5), dict(max_iter=0), dict(adapt_rho=1, adapt_tau=1.0),
+                dict(precision="tf32"), dict(xupdate="dense", history=1)):
+        with pytest.raises(pkg.AdmmError) as e:
+            solver.solve(prob, dict(opts, **bad))
+        assert e.value.code == E
+    bt = prob["block_type"].copy()
+    bt[2] = 99
+    with pytest.raises(pkg.AdmmError):
+        solver.solve(dict(prob, block_type=bt), opts)
+    bt = prob["block_type"].copy()
+    bt[2] = P.BLK_NONE                                       # unsplit control without R: singular x-update
+    with pytest.raises(pkg.AdmmError):
+        solver.solve(dict(prob, block_type=bt), opts)
+    with pytest.raises(pkg.AdmmError) as e:
+        pkg.Solver().download(opts)
+    assert e.value.code == pkg._lib.E_STATE
+    # a NaN input is a per-problem status, never an error of the call
+    prob["s0"][1, 0] = np.nan
+    x, z, u, h = solver.solve(prob, dict(opts, max_iter=20))
+    assert h["status"][1] == 2 and h["status"][0] != 2
+
+
+def test_full_size_cfg2_properties(solver, cpu_oracle, P):
+    """configs[1] at full size (4,096 x N=50): size-independent properties + oracle parity on a slice."""
+    from oracle import admm_ocp as O
+    prob, opts = P.cfg2_cw_batch(batch=4096, N=50, seed=2)
+    opts = dict(opts, max_iter=600)
+    x, z, u, h = solver.solve(prob, opts)
+    N, n = 50, 456
+    G = O.assemble_G(prob["A"][0], prob["B"][0], N)
+    hv = np.zeros((4096, 6 * (N + 1)))
+    hv[:, :6] = prob["s0"]
+    assert np.abs(x @ G.T - hv).max() < 1e-9                 # every x satisfies the dynamics
+    zb = z.reshape(4096, -1, 3)
+    assert np.all(np.abs(zb[:, 2:3 * N:3]) <= 0.4 + 1e-15)   # z inside the dv box
+    assert np.all(zb[:, 3 * N:] == 0.0)                      # terminal point
+    sl = slice(1000, 1064)
+    sub = dict(prob, s0=prob["s0"][sl])
+    xr, zr, ur, hr = cpu_oracle.solve(sub, opts)
+    assert np.array_equal(h["iters"][sl], hr["iters"])
+    assert np.array_equal(x[sl], xr) and np.array_equal(z[sl], zr) and np.array_equal(u[sl], ur)
