@@ -11,6 +11,7 @@
 #include <new>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <mutex>
 #include <string>
@@ -133,8 +134,8 @@ struct Shard {
     void download(admmb_result *res);
     template <bool FSH, bool FSMEM>
     void launch_iterate(const IterParams &P, bool adapt);
-    template <class K>
-    void launch_iterate_kernel(K kern, const IterParams &P, size_t smem);
+    template <class K1, class K2>
+    void launch_iterate_kernel(K1 kern, K2 kern_lowocc, const IterParams &P, size_t smem);
 };
 
 void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt)
@@ -184,8 +185,9 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     for (int k = 0; k < N; ++k)
         fast_pattern = fast_pattern && pb->block_type[3 * k] == BLK_NONE && pb->block_type[3 * k + 1] == BLK_NONE &&
                        pb->block_type[3 * k + 2] != BLK_NONE;
-    bdesc.alloc(nb);
+    bdesc.alloc(((size_t)nb + 3) / 4 * 4);   // padded: staged into smem with a 16-byte-granular bulk copy
     rowmap.alloc(n);
+    CK(cudaMemsetAsync(bdesc.p, 0, sizeof(int) * (((size_t)nb + 3) / 4 * 4), stream));
     CK(cudaMemcpyAsync(bdesc.p, h_bdesc.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(rowmap.p, h_rowmap.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream));
 
@@ -255,28 +257,38 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     uploaded = true;
 }
 
+// smallest CTA that still puts every active problem on the machine in one wave; otherwise the CTA
+// size with the largest resident capacity.  Returns the resident capacity in *cap_out.
 template <class K>
-void Shard::launch_iterate_kernel(K kern, const IterParams &P, size_t smem)
+static int pick_block(K kern, size_t smem, int num_sms, int n_active, long *cap_out)
 {
-    static thread_local const void *configured[64];
-    static thread_local int n_configured = 0;
-    bool seen = false;
-    for (int i = 0; i < n_configured; ++i) seen |= configured[i] == (const void *)kern;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!seen && n_configured < 64) configured[n_configured++] = (const void *)kern;
-    // smallest CTA that still puts every active problem on the machine in one wave; otherwise the
-    // CTA size with the largest resident capacity (grid sized in whole waves by the block scheduler)
-    int bestT = 128, best_cap = -1;
+    int bestT = 128;
+    long best_cap = -1;
     for (int T = 32; T <= 256; T += 32) {
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
-        if (occ <= 0) continue;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem) != cudaSuccess || occ <= 0) continue;
         long cap = (long)occ * num_sms * T;
-        if ((long)P.n_active <= cap) { bestT = T; best_cap = -2; break; }
-        if (cap > best_cap) { best_cap = (int)cap; bestT = T; }
+        if ((long)n_active <= cap) { *cap_out = cap; return T; }
+        if (cap > best_cap) { best_cap = cap; bestT = T; }
     }
-    int grid = (P.n_active + bestT - 1) / bestT;
-    kern<<<grid, bestT, smem, stream>>>(P);
+    *cap_out = best_cap;
+    return bestT;
+}
+
+template <class K1, class K2>
+void Shard::launch_iterate_kernel(K1 kern, K2 kern_lowocc, const IterParams &P, size_t smem)
+{
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern_lowocc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the uncapped-register build when it still holds the whole active set in one wave
+    long cap_lo = 0, cap_hi = 0;
+    const int T_lo = pick_block(kern_lowocc, smem, num_sms, P.n_active, &cap_lo);
+    if ((long)P.n_active <= cap_lo) {
+        kern_lowocc<<<(P.n_active + T_lo - 1) / T_lo, T_lo, smem, stream>>>(P);
+    } else {
+        const int T = pick_block(kern, smem, num_sms, P.n_active, &cap_hi);
+        kern<<<(P.n_active + T - 1) / T, T, smem, stream>>>(P);
+    }
     ++launches;
     CK(cudaGetLastError());
 }
@@ -284,13 +296,17 @@ void Shard::launch_iterate_kernel(K kern, const IterParams &P, size_t smem)
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
-    size_t smem = ((FSH && FSMEM) ? sizeof(double) * FS * N : 0) + (par_batched ? 0 : sizeof(double) * 8 * nb) +
-                  sizeof(int) * nb;
+    size_t smem = 16 + ((FSH && FSMEM) ? sizeof(double) * FS * N : 0) + (par_batched ? 0 : sizeof(double) * 8 * nb) +
+                  sizeof(int) * ((nb + 3) / 4) * 4;
     smem = round_up(smem, 16);
-#define DISPATCH(C, Q, A)                                                                      \
-    do {                                                                                      \
-        if (fast_pattern) launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, true>, P, smem);  \
-        else launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, false>, P, smem);              \
+#define DISPATCH(C, Q, A)                                                                       \
+    do {                                                                                       \
+        if (fast_pattern)                                                                      \
+            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, true, false>,            \
+                                  k_admm_iterate<FSH, FSMEM, C, Q, A, true, true>, P, smem);   \
+        else                                                                                   \
+            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, false, false>,           \
+                                  k_admm_iterate<FSH, FSMEM, C, Q, A, false, true>, P, smem);  \
     } while (0)
     if (has_c) {
         if (has_q) { if (adapt) DISPATCH(true, true, true); else DISPATCH(true, true, false); }
@@ -375,7 +391,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         if (adapt && P.every < chunk && P.every > 0) chunk = (chunk / P.every) * P.every;   // keep launches aligned
         if (chunk < 1) chunk = 1;
         P.chunk = chunk;
-        const bool fsmem = shared_factor && sizeof(double) * FS * N + sizeof(double) * 8 * nb + 4 * nb <= 200 * 1024;
+        const bool fsmem = shared_factor && sizeof(double) * FS * N + sizeof(double) * 8 * nb + 4 * nb + 64 <= 200 * 1024;
 
         int *cur = active0.p, *nxt = active1.p;
         int n_act = (int)batch;

@@ -214,7 +214,10 @@ __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv,
         const double kap = par(PAR_LAM) * rinv;
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            double t = v[e] > kap ? v[e] - kap : (v[e] < -kap ? v[e] + kap : 0.0);
+            // soft threshold without branches: |v| - kap equals v - kap (v > kap) and -(v + kap)
+            // (v < -kap) bit for bit, so this is the oracle's three-way form as two selects
+            const double m = fabs(v[e]) - kap;
+            double t = m > 0.0 ? copysign(m, v[e]) : 0.0;
             if (type == BLK_L1_BOX) {
                 double lo = par(PAR_LO + e), hi = par(PAR_HI + e);
                 t = t < lo ? lo : (t > hi ? hi : t);
@@ -307,12 +310,26 @@ template <bool SHARED>
 struct FacRef {
     const double *base;
     size_t ld;
+    uint32_t sbase;               // shared-window address of the staged factor (0 when not in smem)
     __device__ __forceinline__ double operator()(int k, int off) const
     {
         if (SHARED) return base[k * FS + off];
         return base[((size_t)k * FS + off) * ld];
     }
 };
+
+__device__ __forceinline__ double2 lds128(uint32_t a)
+{
+    double2 r;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ double lds64(uint32_t a)
+{
+    double r;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // One ADMM iteration of problem p (rows a2 + a3 + a4 fused): backward sweep, then a forward sweep
@@ -475,24 +492,32 @@ __device__ __forceinline__ void admm_iteration(const IterParams &P, const size_t
 //   * factor rows are read with 128-bit loads (LDS.128 when the factor is staged in shared memory).
 // Operation order per accumulator is exactly that of admm_iteration / the oracle.
 // ------------------------------------------------------------------------------------------------
-template <bool FSH>
+template <bool FSH, bool FSMEM>
 __device__ __forceinline__ void fac_row6(const FacRef<FSH> &F, int k, int off, double (&r)[6])
 {
-    if (FSH) {
+    if (FSH && FSMEM) {
+        const uint32_t a = F.sbase + (uint32_t)(k * FS + off) * 8u;
+        const double2 x = lds128(a), y = lds128(a + 16), z = lds128(a + 32);
+        r[0] = x.x; r[1] = x.y; r[2] = y.x; r[3] = y.y; r[4] = z.x; r[5] = z.y;
+    } else if (FSH) {
         const double2 *q = reinterpret_cast<const double2 *>(F.base + k * FS + off);
-        const double2 a = q[0], b = q[1], c = q[2];
+        const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
         r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i) r[i] = F.base[((size_t)k * FS + off + i) * F.ld];
     }
 }
-template <bool FSH>
+template <bool FSH, bool FSMEM>
 __device__ __forceinline__ void fac_row3(const FacRef<FSH> &F, int k, int off, double (&r)[3])
 {
-    if (FSH) {   // rows of Hinv and B are padded to 4 doubles
+    if (FSH && FSMEM) {   // rows of Hinv and B are padded to 4 doubles
+        const uint32_t a = F.sbase + (uint32_t)(k * FS + off) * 8u;
+        const double2 x = lds128(a), y = lds128(a + 16);
+        r[0] = x.x; r[1] = x.y; r[2] = y.x;
+    } else if (FSH) {
         const double2 *q = reinterpret_cast<const double2 *>(F.base + k * FS + off);
-        const double2 a = q[0], b = q[1];
+        const double2 a = __ldg(q), b = __ldg(q + 1);
         r[0] = a.x; r[1] = a.y; r[2] = b.x;
     } else {
 #pragma unroll
@@ -530,24 +555,31 @@ __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, d
     }
 }
 
-template <bool FSH, bool HAS_C, bool HAS_Q, bool ADAPT>
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT>
 __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const size_t p, const FacRef<FSH> F,
-                                                    const int *bdesc, const double *parS, const double rho,
+                                                    const int *bdesc, const uint32_t par_sbase, const double rho,
                                                     const double sigma, double (&nr)[5])
 {
     const int N = P.N;
     const size_t ld = P.ld;
     const double rinv = 1.0 / rho;
-    double *zp = P.z + p, *up = P.u + p, *dp = P.d + p;
+    // in this pattern the split blocks are ctrl_0 .. ctrl_{N-1} followed by the terminal blocks, so the
+    // compact z/u rows of ctrl_k are 3k..3k+2: plain pointer walks, no index arithmetic in the loops
+    const ptrdiff_t ld1 = (ptrdiff_t)ld, ld2 = 2 * (ptrdiff_t)ld, ld3 = 3 * (ptrdiff_t)ld;
+    double *const zp = P.z + p, *const up = P.u + p, *const dp = P.d + p;
     const double *qp = HAS_Q ? (P.q_batched ? P.q + p : P.q) : nullptr;
     const size_t qld = P.q_batched ? ld : 1;
 
-    auto load_ctrl = [&](int k, double (&zc)[3], double (&uc)[3]) {
-        const size_t r0 = (size_t)(bdesc[3 * k + 2] >> 8) * 3;
+    // parameters of block b into registers (shared table: four 128-bit shared loads)
+    auto load_par = [&](int b, double (&pr)[8]) {
+        if (P.par_batched) {
+            const double *pp = P.par + p + (size_t)(8 * b) * ld;
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            zc[e] = __ldcs(zp + (r0 + e) * ld);
-            uc[e] = __ldcs(up + (r0 + e) * ld);
+            for (int q = 0; q < 8; ++q) pr[q] = pp[(size_t)q * ld];
+        } else {
+            const uint32_t a = par_sbase + (uint32_t)b * 64u;
+            const double2 x = lds128(a), y = lds128(a + 16), z = lds128(a + 32), w = lds128(a + 48);
+            pr[0] = x.x; pr[1] = x.y; pr[2] = y.x; pr[3] = y.y; pr[4] = z.x; pr[5] = z.y; pr[6] = w.x; pr[7] = w.y;
         }
     };
     auto rt_terminal = [&](int b, double (&t)[3]) {
@@ -568,18 +600,29 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
         }
     };
 
-    // ---------------- backward sweep
-    double g[6];
+    // ---------------- backward sweep: two register buffers, prefetch distance two stages
+    double gA[6], gB[6];
     {
         double t0[3], t1[3];
         rt_terminal(3 * N, t0);
         rt_terminal(3 * N + 1, t1);
-        g[0] = t0[0]; g[1] = t0[1]; g[2] = t0[2]; g[3] = t1[0]; g[4] = t1[1]; g[5] = t1[2];
+        gA[0] = t0[0]; gA[1] = t0[1]; gA[2] = t0[2]; gA[3] = t1[0]; gA[4] = t1[1]; gA[5] = t1[2];
     }
-    double zc[3], uc[3];
-    load_ctrl(N - 1, zc, uc);
-    for (int k = N - 1; k >= 0; --k) {
-        double ra[3], pn[6], zn[3], un[3];
+    double zA[3], uA[3], zB[3], uB[3];
+    {
+        const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
+        zA[0] = __ldcs(z0); zA[1] = __ldcs(z0 + ld1); zA[2] = __ldcs(z0 + ld2);
+        uA[0] = __ldcs(u0); uA[1] = __ldcs(u0 + ld1); uA[2] = __ldcs(u0 + ld2);
+        if (N > 1) {
+            z0 -= ld3; u0 -= ld3;
+            zB[0] = __ldcs(z0); zB[1] = __ldcs(z0 + ld1); zB[2] = __ldcs(z0 + ld2);
+            uB[0] = __ldcs(u0); uB[1] = __ldcs(u0 + ld1); uB[2] = __ldcs(u0 + ld2);
+        }
+    }
+    const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;   // rows of stage k-2
+    double *ds = dp + (ptrdiff_t)(N - 1) * ld3;                                               // rows of stage k
+    auto bwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], const double (&g)[6], double (&pn)[6]) {
+        double ra[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             double uu = ADAPT ? uc[e] * sigma : uc[e];
@@ -587,96 +630,114 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             if (HAS_Q) v = fma(-qp[(size_t)(9 * k + 6 + e) * qld], rinv, v);
             ra[e] = v;
         }
-        if (k > 0) load_ctrl(k - 1, zn, un);
+        if (k >= 2) {   // refill this buffer with the stage two steps ahead
+            zc[0] = __ldcs(zl); zc[1] = __ldcs(zl + ld1); zc[2] = __ldcs(zl + ld2);
+            uc[0] = __ldcs(ul); uc[1] = __ldcs(ul + ld1); uc[2] = __ldcs(ul + ld2);
+        }
+        zl -= ld3; ul -= ld3;
+        double gg[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) pn[i] = HAS_Q ? -(qp[(size_t)(9 * k + i) * qld] * rinv) : 0.0;
+        for (int i = 0; i < 6; ++i) gg[i] = g[i];
         if (HAS_C) {
             double ch[6];
-            fac_row6(F, k, F_CHAT, ch);
+            fac_row6<FSH, FSMEM>(F, k, F_CHAT, ch);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = g[i] - ch[i];
+            for (int i = 0; i < 6; ++i) gg[i] = gg[i] - ch[i];
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pn[i] = HAS_Q ? -(qp[(size_t)(9 * k + i) * qld] * rinv) : 0.0;
+        double dj[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             double h[3], er[6];
-            fac_row3(F, k, F_HINV + HINV_LD * j, h);
-            fac_row6(F, k, F_E + 6 * j, er);
+            fac_row3<FSH, FSMEM>(F, k, F_HINV + HINV_LD * j, h);
+            fac_row6<FSH, FSMEM>(F, k, F_E + 6 * j, er);
             double acc = h[0] * ra[0];
             acc = fma(h[1], ra[1], acc);
             acc = fma(h[2], ra[2], acc);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) acc = fma(er[i], g[i], acc);
-            __stcs(dp + (size_t)(3 * k + j) * ld, acc);
+            for (int i = 0; i < 6; ++i) acc = fma(er[i], gg[i], acc);
+            dj[j] = acc;
         }
+        __stcs(ds, dj[0]); __stcs(ds + ld1, dj[1]); __stcs(ds + ld2, dj[2]);
+        ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             double kr[6];
-            fac_row6(F, k, F_K + 6 * j, kr);
+            fac_row6<FSH, FSMEM>(F, k, F_K + 6 * j, kr);
 #pragma unroll
             for (int i = 0; i < 6; ++i) pn[i] = fma(kr[i], ra[j], pn[i]);
         }
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
             double ar[6];
-            fac_row6(F, k, F_ACL + 6 * l, ar);
+            fac_row6<FSH, FSMEM>(F, k, F_ACL + 6 * l, ar);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) pn[i] = fma(ar[i], g[l], pn[i]);
+            for (int i = 0; i < 6; ++i) pn[i] = fma(ar[i], gg[l], pn[i]);
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] = pn[i];
-        if (k > 0) {
-#pragma unroll
-            for (int e = 0; e < 3; ++e) { zc[e] = zn[e]; uc[e] = un[e]; }
+    };
+    {
+        int k = N - 1;
+        for (; k >= 1; k -= 2) {
+            bwd_stage(k, zA, uA, gA, gB);
+            bwd_stage(k - 1, zB, uB, gB, gA);
         }
+        if (k == 0) bwd_stage(0, zA, uA, gA, gB);
     }
 
     // ---------------- forward sweep fused with prox / dual ascent / norms
     double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
-    double s[6], dk[3];
+    double sA[6], sB[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) s[i] = P.s0[p + (size_t)i * ld];
-    load_ctrl(0, zc, uc);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) dk[j] = __ldcs(dp + (size_t)j * ld);
-    for (int k = 0; k < N; ++k) {
-        double a[3], sn[6], zn[3], un[3], dn[3];
-        if (k + 1 < N) {
-            load_ctrl(k + 1, zn, un);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) dn[j] = __ldcs(dp + (size_t)(3 * (k + 1) + j) * ld);
+    for (int i = 0; i < 6; ++i) sA[i] = P.s0[p + (size_t)i * ld];
+    double dA[3], dB[3];
+    {
+        zA[0] = __ldcs(zp); zA[1] = __ldcs(zp + ld1); zA[2] = __ldcs(zp + ld2);
+        uA[0] = __ldcs(up); uA[1] = __ldcs(up + ld1); uA[2] = __ldcs(up + ld2);
+        dA[0] = __ldcs(dp); dA[1] = __ldcs(dp + ld1); dA[2] = __ldcs(dp + ld2);
+        if (N > 1) {
+            zB[0] = __ldcs(zp + ld3); zB[1] = __ldcs(zp + ld3 + ld1); zB[2] = __ldcs(zp + ld3 + ld2);
+            uB[0] = __ldcs(up + ld3); uB[1] = __ldcs(up + ld3 + ld1); uB[2] = __ldcs(up + ld3 + ld2);
+            dB[0] = __ldcs(dp + ld3); dB[1] = __ldcs(dp + ld3 + ld1); dB[2] = __ldcs(dp + ld3 + ld2);
         }
+    }
+    const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;   // rows of stage k+2 (loads)
+    double *zw = zp, *uw = up, *dw = dp;                                        // rows of stage k (stores)
+    auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&s)[6],
+                         double (&sn)[6]) {
+        double a[3], zo[3], uo[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             double kr[6];
-            fac_row6(F, k, F_K + 6 * j, kr);
-            double acc = dk[j];
+            fac_row6<FSH, FSMEM>(F, k, F_K + 6 * j, kr);
+            double acc = dc[j];
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc = fma(kr[i], s[i], acc);
             a[j] = acc;
-            __stcs(dp + (size_t)(3 * k + j) * ld, acc);
+            zo[j] = zc[j];
+            uo[j] = ADAPT ? uc[j] * sigma : uc[j];
         }
+        if (k + 2 < N) {   // refill this buffer with the stage two steps ahead
+            zc[0] = __ldcs(zf); zc[1] = __ldcs(zf + ld1); zc[2] = __ldcs(zf + ld2);
+            uc[0] = __ldcs(uf); uc[1] = __ldcs(uf + ld1); uc[2] = __ldcs(uf + ld2);
+            dc[0] = __ldcs(df); dc[1] = __ldcs(df + ld1); dc[2] = __ldcs(df + ld2);
+        }
+        zf += ld3; uf += ld3; df += ld3;
+        __stcs(dw, a[0]); __stcs(dw + ld1, a[1]); __stcs(dw + ld2, a[2]);
+        dw += ld3;
         {
             const int b = 3 * k + 2;
-            const int de = bdesc[b];
-            const size_t r0 = (size_t)(de >> 8) * 3;
-            double uo[3];
-#pragma unroll
-            for (int e = 0; e < 3; ++e) uo[e] = ADAPT ? uc[e] * sigma : uc[e];
-            if (P.par_batched) {
-                const double *pp = P.par + p + (size_t)(8 * b) * ld;
-                block_update(de & 0xff, [&](int q) { return pp[(size_t)q * ld]; }, rinv, P.alpha, P.oma, a, zc, uo,
-                             zp + r0 * ld, up + r0 * ld, ld, rr, ss, xx, zz, uu);
-            } else {
-                const double *pp = parS + 8 * b;
-                block_update(de & 0xff, [&](int q) { return pp[q]; }, rinv, P.alpha, P.oma, a, zc, uo,
-                             zp + r0 * ld, up + r0 * ld, ld, rr, ss, xx, zz, uu);
-            }
+            double pr[8];
+            load_par(b, pr);
+            block_update(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ld, rr,
+                         ss, xx, zz, uu);
+            zw += ld3; uw += ld3;
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             double ar[6], br[3];
-            fac_row6(F, k, F_A + 6 * i, ar);
-            fac_row3(F, k, F_B + B_LD * i, br);
+            fac_row6<FSH, FSMEM>(F, k, F_A + 6 * i, ar);
+            fac_row3<FSH, FSMEM>(F, k, F_B + B_LD * i, br);
             double acc = ar[0] * s[0];
 #pragma unroll
             for (int l = 1; l < 6; ++l) acc = fma(ar[l], s[l], acc);
@@ -685,12 +746,15 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             if (HAS_C) acc = acc + F(k, F_C + i);
             sn[i] = acc;
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) s[i] = sn[i];
-        if (k + 1 < N) {
-#pragma unroll
-            for (int e = 0; e < 3; ++e) { zc[e] = zn[e]; uc[e] = un[e]; dk[e] = dn[e]; }
+    };
+    bool s_in_A = true;
+    {
+        int k = 0;
+        for (; k + 1 < N; k += 2) {
+            fwd_stage(k, zA, uA, dA, sA, sB);
+            fwd_stage(k + 1, zB, uB, dB, sB, sA);
         }
+        if (k < N) { fwd_stage(k, zA, uA, dA, sA, sB); s_in_A = false; }
     }
     // terminal blocks (arbitrary types)
 #pragma unroll
@@ -699,25 +763,49 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
         const int de = bdesc[b];
         if ((de & 0xff) == BLK_NONE) continue;
         const size_t r0 = (size_t)(de >> 8) * 3;
-        const double xb[3] = {s[3 * t], s[3 * t + 1], s[3 * t + 2]};
-        double zo[3], uo[3];
+        const double xb[3] = {s_in_A ? sA[3 * t] : sB[3 * t], s_in_A ? sA[3 * t + 1] : sB[3 * t + 1],
+                              s_in_A ? sA[3 * t + 2] : sB[3 * t + 2]};
+        double zo[3], uo[3], pr[8];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             zo[e] = __ldcs(zp + (r0 + e) * ld);
             double uv = __ldcs(up + (r0 + e) * ld);
             uo[e] = ADAPT ? uv * sigma : uv;
         }
-        if (P.par_batched) {
-            const double *pp = P.par + p + (size_t)(8 * b) * ld;
-            block_update(de & 0xff, [&](int q) { return pp[(size_t)q * ld]; }, rinv, P.alpha, P.oma, xb, zo, uo,
-                         zp + r0 * ld, up + r0 * ld, ld, rr, ss, xx, zz, uu);
-        } else {
-            const double *pp = parS + 8 * b;
-            block_update(de & 0xff, [&](int q) { return pp[q]; }, rinv, P.alpha, P.oma, xb, zo, uo,
-                         zp + r0 * ld, up + r0 * ld, ld, rr, ss, xx, zz, uu);
-        }
+        load_par(b, pr);
+        block_update(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ld,
+                     up + r0 * ld, ld, rr, ss, xx, zz, uu);
     }
     nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous global array into shared memory,
+// completion signalled on an mbarrier: one instruction stages the whole 62 KB factor table.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -725,21 +813,33 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
 // its problem, evaluates the stopping test on device, leaves as soon as its problem is done
 // (per-problem early exit) and applies the residual-balancing rho update, refactorising only its
 // own problem when the factor depends on rho.
-// dynamic smem: [FSH ? FS*N : 0] factor, [par shared ? 8*nb : 0] parameters, [nb] block descriptors
+// dynamic smem: [16 B mbarrier][FSH && FSMEM ? FS*N doubles : 0][par shared ? 8*nb doubles : 0][nb ints]
+// LOWOCC: variant compiled without the 128-register cap, used when the active set is small enough
+// that occupancy does not matter (no spills of the prefetch registers).
 // ------------------------------------------------------------------------------------------------
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, bool FAST>
-__global__ void __launch_bounds__(256) k_admm_iterate(const __grid_constant__ IterParams P)
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, bool FAST, bool LOWOCC>
+__global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __grid_constant__ IterParams P)
 {
-    extern __shared__ __align__(16) double smem[];
-    double *facS = smem;   // dynamic smem is 16-byte aligned: 128-bit factor loads are legal
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *facS = reinterpret_cast<double *>(smem_raw + 16);
     double *parS = facS + ((FSH && FSMEM) ? (size_t)FS * P.N : 0);
-    int *bdS = (int *)(parS + (P.par_batched ? 0 : 8 * P.nb));
-    if (FSH && FSMEM)
-        for (int i = threadIdx.x; i < FS * P.N; i += blockDim.x) facS[i] = P.fac[i];
-    if (!P.par_batched)
-        for (int i = threadIdx.x; i < 8 * P.nb; i += blockDim.x) parS[i] = P.par[i];
-    for (int i = threadIdx.x; i < P.nb; i += blockDim.x) bdS[i] = P.bdesc[i];
+    int *bdS = reinterpret_cast<int *>(parS + (P.par_batched ? 0 : 8 * P.nb));
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t fac_sbase = (uint32_t)__cvta_generic_to_shared(facS);
+    const uint32_t par_sbase = (uint32_t)__cvta_generic_to_shared(parS);
+    const uint32_t bd_bytes = (uint32_t)(((P.nb + 3) / 4) * 16);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        uint32_t bytes = bd_bytes;
+        if (FSH && FSMEM) bytes += (uint32_t)(FS * P.N * 8);
+        if (!P.par_batched) bytes += (uint32_t)(8 * P.nb * 8);
+        mbar_expect_tx(mbar, bytes);
+        if (FSH && FSMEM) bulk_g2s(fac_sbase, P.fac, (uint32_t)(FS * P.N * 8), mbar);
+        if (!P.par_batched) bulk_g2s(par_sbase, P.par, (uint32_t)(8 * P.nb * 8), mbar);
+        bulk_g2s((uint32_t)__cvta_generic_to_shared(bdS), P.bdesc, bd_bytes, mbar);
+    }
     __syncthreads();
+    mbar_wait(mbar, 0);
 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n_active) return;
@@ -749,6 +849,7 @@ __global__ void __launch_bounds__(256) k_admm_iterate(const __grid_constant__ It
     FacRef<FSH> F;
     F.base = FSH ? (FSMEM ? facS : P.fac) : P.fac + p;
     F.ld = P.ld;
+    F.sbase = fac_sbase;
 
     double rho = P.rho[p];
     double sigma = ADAPT ? P.usc[p] : 1.0;
@@ -758,7 +859,7 @@ __global__ void __launch_bounds__(256) k_admm_iterate(const __grid_constant__ It
     for (int cnt = 0; cnt < P.chunk && st == ST_RUNNING; ++cnt) {
         ++it;
         double nr[5];
-        if (FAST) admm_iteration_fast<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
+        if (FAST) admm_iteration_fast<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else admm_iteration<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
         sigma = 1.0;
         r_norm = sqrt(nr[0]);
