@@ -58,12 +58,21 @@ struct Shard {
         CK(cudaEventRecord(kev[kev_used], stream));
     }
     void kernel_toc() { CK(cudaEventRecord(kev[kev_used + 1], stream)); kev_used += 2; }
+    std::vector<int> trace_active;    // ADMMB_TRACE=1: active problems per launch
     void kernel_collect()   // after a stream sync
     {
         kernel_ms = 0.0;
         kernel_launches = (int64_t)(kev_used / 2);
-        for (size_t i = 0; i < kev_used; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, kev[i], kev[i + 1])); kernel_ms += ms; }
+        const bool trace = getenv("ADMMB_TRACE") != nullptr;
+        for (size_t i = 0; i < kev_used; i += 2) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, kev[i], kev[i + 1]));
+            kernel_ms += ms;
+            if (trace && i / 2 < trace_active.size())
+                fprintf(stderr, "[admmb trace] launch %zu: active %d, %.3f ms\n", i / 2, trace_active[i / 2], ms);
+        }
         kev_used = 0;
+        trace_active.clear();
     }
 
     // problem shape
@@ -75,13 +84,42 @@ struct Shard {
     bool shared_factor = true, uploaded = false, ran = false;
     bool use_dense = false;
     bool fast_pattern = false;   // stage states unsplit, every control split: prefetching kernel variant
+    bool decoupled = false;      // in-plane / cross-track structure proven on the factor: packed records
     int max_iter_alloc = 0;
     bool hist_alloc = false;
 
     std::vector<int> h_bdesc, h_rowmap;
-    DevBuf<double> rawA, rawB, rawc, rawQ, rawR, fac, s0, z, u, d, q, par, z0c, u0c, rho, rho0, usc, fin,
+    DevBuf<double> rawA, rawB, rawc, rawQ, rawR, fac, fac_dec, s0, z, u, d, q, par, z0c, u0c, rho, rho0, usc, fin,
         hist, xo, zo, uo, stage;
-    DevBuf<int> bdesc, rowmap, active0, active1, n_active, iters, status, fac_status, istage;
+    DevBuf<int> dec_flag, bdesc, rowmap, iters, status, fac_status, istage;
+    // the working set: per-problem arrays that travel with the still-running problems (physical
+    // compaction); set -1 = the home arrays themselves, 0/1 = dense ping-pong copies
+    enum { C_Z, C_U, C_D, C_S0, C_RHO, C_USC, C_ITERS, C_STATUS, C_FIN, C_Q, C_PAR, C_FAC, C_FACDEC, C_RAWA, C_RAWB,
+           C_RAWC, C_RAWQ, C_RAWR, C_COUNT };
+    struct ColArray {
+        void *home = nullptr;
+        size_t elem = 8;
+        int rows = 0;          // 0: array absent / shared (does not travel)
+        bool retire = false;   // written by the solver: finished problems copy it back to their home column
+        DevBuf<unsigned char> work[2];
+    };
+    ColArray cols[C_COUNT];
+    DevBuf<int> orig[2], keep_list, fin_list, split_counts;
+    int cur_set = -1;
+    int64_t width = 0;
+    size_t ld_cur = 0;
+    template <typename T>
+    T *colptr(int c) const
+    {
+        const ColArray &a = cols[c];
+        if (a.rows == 0 || cur_set < 0) return (T *)a.home;
+        return (T *)a.work[cur_set].p;
+    }
+    void set_col(int c, void *home, size_t elem, int rows, bool retire)
+    {
+        cols[c].home = home; cols[c].elem = elem; cols[c].rows = home ? rows : 0; cols[c].retire = retire;
+    }
+    void repack(int n_keep, int n_fin);
     DevBuf<unsigned long long> counters;   // [0] refactor count, [1] converged, [2] sum iters, [3] max iters
     DenseState dense;
 
@@ -239,9 +277,9 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     iters.alloc(ld);
     status.alloc(ld);
     fac_status.alloc(ld);
-    active0.alloc(ld);
-    active1.alloc(ld);
-    n_active.alloc(1);
+    keep_list.alloc(ld);
+    fin_list.alloc(ld);
+    split_counts.alloc(2);
     counters.alloc(4);
     CK(cudaMemsetAsync(fac_status.p, 0, sizeof(int) * ld, stream));
     CK(cudaMemsetAsync(d.p, 0, sizeof(double) * 3 * N * ld, stream));
@@ -296,17 +334,21 @@ void Shard::launch_iterate_kernel(K1 kern, K2 kern_lowocc, const IterParams &P, 
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
-    size_t smem = 16 + ((FSH && FSMEM) ? sizeof(double) * FS * N : 0) + (par_batched ? 0 : sizeof(double) * 8 * nb) +
+    size_t smem = 16 + ((FSH && FSMEM) ? sizeof(double) * (decoupled ? FD : FS) * N : 0) +
+                  (par_batched ? 0 : sizeof(double) * 8 * nb) +
                   sizeof(int) * ((nb + 3) / 4) * 4;
     smem = round_up(smem, 16);
 #define DISPATCH(C, Q, A)                                                                       \
     do {                                                                                       \
-        if (fast_pattern)                                                                      \
-            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, true, false>,            \
-                                  k_admm_iterate<FSH, FSMEM, C, Q, A, true, true>, P, smem);   \
+        if (fast_pattern && decoupled)                                                         \
+            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 2, false>,               \
+                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 2, true>, P, smem);      \
+        else if (fast_pattern)                                                                 \
+            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 1, false>,               \
+                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 1, true>, P, smem);      \
         else                                                                                   \
-            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, false, false>,           \
-                                  k_admm_iterate<FSH, FSMEM, C, Q, A, false, true>, P, smem);  \
+            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 0, false>,               \
+                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 0, true>, P, smem);      \
     } while (0)
     if (has_c) {
         if (has_q) { if (adapt) DISPATCH(true, true, true); else DISPATCH(true, true, false); }
@@ -316,6 +358,53 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
         else { if (adapt) DISPATCH(false, false, true); else DISPATCH(false, false, false); }
     }
 #undef DISPATCH
+}
+
+// retire the finished columns of the working set to their home columns and move the still-running
+// ones into a dense, 32-aligned prefix of the other ping-pong buffer
+void Shard::repack(int n_keep, int n_fin)
+{
+    const unsigned gf = (unsigned)((n_fin + 127) / 128), gk = (unsigned)((n_keep + 127) / 128);
+    auto rows_grid = [](int rows) { return (unsigned)std::min(rows, 64); };
+    if (cur_set >= 0 && n_fin > 0) {
+        for (int c = 0; c < C_COUNT; ++c) {
+            ColArray &a = cols[c];
+            if (a.rows == 0 || !a.retire) continue;
+            dim3 grid(gf, rows_grid(a.rows));
+            if (a.elem == 8)
+                k_scatter_cols<double><<<grid, 128, 0, stream>>>((const double *)a.work[cur_set].p, ld_cur, a.rows,
+                                                                 fin_list.p, n_fin, orig[cur_set].p, (double *)a.home, ld);
+            else
+                k_scatter_cols<int><<<grid, 128, 0, stream>>>((const int *)a.work[cur_set].p, ld_cur, a.rows, fin_list.p,
+                                                              n_fin, orig[cur_set].p, (int *)a.home, ld);
+            ++launches;
+        }
+        CK(cudaGetLastError());
+    }
+    if (n_keep == 0) { width = 0; return; }
+    const int nxt = cur_set == 0 ? 1 : 0;
+    const size_t ld_new = round_up((size_t)n_keep, 32);
+    orig[nxt].alloc(ld_new);
+    k_compose_orig<<<gk, 128, 0, stream>>>(cur_set < 0 ? nullptr : orig[cur_set].p, keep_list.p, n_keep, orig[nxt].p);
+    ++launches;
+    for (int c = 0; c < C_COUNT; ++c) {
+        ColArray &a = cols[c];
+        if (a.rows == 0) continue;
+        a.work[nxt].alloc((size_t)a.rows * ld_new * a.elem);
+        const void *src = cur_set < 0 ? a.home : (const void *)a.work[cur_set].p;
+        dim3 grid(gk, rows_grid(a.rows));
+        if (a.elem == 8)
+            k_gather_cols<double><<<grid, 128, 0, stream>>>((const double *)src, ld_cur, a.rows, keep_list.p, n_keep,
+                                                            (double *)a.work[nxt].p, ld_new);
+        else
+            k_gather_cols<int><<<grid, 128, 0, stream>>>((const int *)src, ld_cur, a.rows, keep_list.p, n_keep,
+                                                         (int *)a.work[nxt].p, ld_new);
+        ++launches;
+    }
+    CK(cudaGetLastError());
+    cur_set = nxt;
+    width = n_keep;
+    ld_cur = ld_new;
 }
 
 __global__ void k_stats(int64_t batch, const int *iters, const int *status, unsigned long long *counters)
@@ -358,6 +447,24 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     }
     ++launches;
     CK(cudaGetLastError());
+    decoupled = false;
+    if (fast_pattern && !use_dense && getenv("ADMMB_NO_DECOUPLED") == nullptr) {
+        const int64_t nf = shared_factor ? 1 : batch;
+        dec_flag.alloc(1);
+        CK(cudaMemsetAsync(dec_flag.p, 0, sizeof(int), stream));
+        k_check_decoupled<<<(unsigned)((nf + 127) / 128), 128, 0, stream>>>(N, nf, shared_factor ? 0 : 1, fac.p, ld, dec_flag.p);
+        ++launches;
+        int flag = 1;
+        CK(cudaMemcpyAsync(&flag, dec_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (flag == 0) {
+            decoupled = true;
+            fac_dec.alloc(shared_factor ? (size_t)FD * N : (size_t)FD * N * ld);
+            k_pack_decoupled<<<(unsigned)((nf + 127) / 128), 128, 0, stream>>>(N, nf, shared_factor ? 0 : 1, fac.p, ld, fac_dec.p);
+            ++launches;
+            CK(cudaGetLastError());
+        }
+    }
     k_reset<<<gb, 128, 0, stream>>>(batch, ld, rows_zu, z.p, u.p, has_z0 ? z0c.p : nullptr,
                                     has_u0 ? u0c.p : nullptr, rho.p, has_rho0 ? rho0.p : nullptr, op->rho, usc.p,
                                     iters.p, status.p, fac_status.p);
@@ -367,20 +474,15 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     if (use_dense) {
         dense_run(*this, op);
     } else {
-        k_iota<<<gb, 128, 0, stream>>>(active0.p, (int)batch);
-        ++launches;
         IterParams P;
         memset(&P, 0, sizeof(P));
-        P.N = N; P.nb = nb; P.n = n; P.ld = ld;
-        P.fac = fac.p; P.fac_rw = fac.p;
-        P.rawA = rawA.p; P.rawB = rawB.p; P.rawc = rawc.p; P.rawQ = rawQ.p; P.rawR = rawR.p;
+        P.N = N; P.nb = nb; P.n = n;
         P.raw_batched = dyn_batched;
-        P.s0 = s0.p; P.z = z.p; P.u = u.p; P.d = d.p;
-        P.q = has_q ? q.p : nullptr; P.q_batched = q_batched;
-        P.bdesc = bdesc.p; P.par = par.p; P.par_batched = par_batched;
-        P.rho = rho.p; P.usc = usc.p; P.iters = iters.p; P.status = status.p; P.fin = fin.p;
+        P.q_batched = q_batched;
+        P.bdesc = bdesc.p; P.par_batched = par_batched;
         P.hist = op->history ? hist.p : nullptr;
         P.hist_stride = (size_t)op->max_iter * ld;
+        P.hist_ld = ld;
         P.refac_count = counters.p;
         P.alpha = op->alpha; P.oma = 1.0 - op->alpha; P.reltol = op->reltol;
         P.sqrtn_abs = sqrt((double)nsplit) * op->abstol;
@@ -391,26 +493,78 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         if (adapt && P.every < chunk && P.every > 0) chunk = (chunk / P.every) * P.every;   // keep launches aligned
         if (chunk < 1) chunk = 1;
         P.chunk = chunk;
-        const bool fsmem = shared_factor && sizeof(double) * FS * N + sizeof(double) * 8 * nb + 4 * nb + 64 <= 200 * 1024;
+        const bool fsmem = shared_factor &&
+                           sizeof(double) * (decoupled ? FD : FS) * N + sizeof(double) * 8 * nb + 4 * nb + 64 <= 200 * 1024;
 
-        int *cur = active0.p, *nxt = active1.p;
-        int n_act = (int)batch;
+        // which per-problem arrays travel with the working set
+        const bool refac = !shared_factor && has_P && adapt;
+        set_col(C_Z, z.p, 8, rows_zu, true);
+        set_col(C_U, u.p, 8, rows_zu, true);
+        set_col(C_D, d.p, 8, 3 * N, true);
+        set_col(C_S0, s0.p, 8, 6, false);
+        set_col(C_RHO, rho.p, 8, 1, true);
+        set_col(C_USC, usc.p, 8, 1, true);
+        set_col(C_ITERS, iters.p, 4, 1, true);
+        set_col(C_STATUS, status.p, 4, 1, true);
+        set_col(C_FIN, fin.p, 8, 4, true);
+        set_col(C_Q, (has_q && q_batched) ? q.p : nullptr, 8, n, false);
+        set_col(C_PAR, par_batched ? par.p : nullptr, 8, 8 * nb, false);
+        set_col(C_FAC, shared_factor ? nullptr : fac.p, 8, FS * N, refac);
+        set_col(C_FACDEC, (!shared_factor && decoupled) ? fac_dec.p : nullptr, 8, FD * N, false);
+        set_col(C_RAWA, (refac && dyn_batched) ? rawA.p : nullptr, 8, 36 * N, false);
+        set_col(C_RAWB, (refac && dyn_batched) ? rawB.p : nullptr, 8, 18 * N, false);
+        set_col(C_RAWC, (refac && dyn_batched && has_c) ? rawc.p : nullptr, 8, 6 * N, false);
+        set_col(C_RAWQ, (refac && dyn_batched && has_Q) ? rawQ.p : nullptr, 8, 36 * (N + 1), false);
+        set_col(C_RAWR, (refac && dyn_batched && has_R) ? rawR.p : nullptr, 8, 9 * N, false);
+        cur_set = -1;
+        width = batch;
+        ld_cur = ld;
+        const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
+
         int done_iters = 0;
-        while (n_act > 0 && done_iters < op->max_iter) {
-            P.active = cur;
-            P.n_active = n_act;
+        while (width > 0 && done_iters < op->max_iter) {
+            P.ld = ld_cur;
+            P.n_active = (int)width;
+            P.orig = cur_set < 0 ? nullptr : orig[cur_set].p;
+            P.fac = shared_factor ? fac.p : colptr<double>(C_FAC);
+            P.fac_rw = colptr<double>(C_FAC);
+            P.fac_dec = (shared_factor || !decoupled) ? fac_dec.p : colptr<double>(C_FACDEC);
+            P.fac_dec_rw = colptr<double>(C_FACDEC);
+            // shared models keep their single raw copy; per-problem raw models travel only when refactoring
+            P.rawA = cols[C_RAWA].rows ? colptr<double>(C_RAWA) : rawA.p;
+            P.rawB = cols[C_RAWB].rows ? colptr<double>(C_RAWB) : rawB.p;
+            P.rawc = cols[C_RAWC].rows ? colptr<double>(C_RAWC) : rawc.p;
+            P.rawQ = cols[C_RAWQ].rows ? colptr<double>(C_RAWQ) : rawQ.p;
+            P.rawR = cols[C_RAWR].rows ? colptr<double>(C_RAWR) : rawR.p;
+            P.s0 = colptr<double>(C_S0); P.z = colptr<double>(C_Z); P.u = colptr<double>(C_U); P.d = colptr<double>(C_D);
+            P.q = has_q ? (q_batched ? colptr<double>(C_Q) : q.p) : nullptr;
+            P.par = par_batched ? colptr<double>(C_PAR) : par.p;
+            P.rho = colptr<double>(C_RHO); P.usc = colptr<double>(C_USC);
+            P.iters = colptr<int>(C_ITERS); P.status = colptr<int>(C_STATUS); P.fin = colptr<double>(C_FIN);
+            trace_active.push_back((int)width);
             kernel_tic();
             if (shared_factor) { if (fsmem) launch_iterate<true, true>(P, adapt); else launch_iterate<true, false>(P, adapt); }
             else launch_iterate<false, false>(P, adapt);
             kernel_toc();
             done_iters += chunk;
-            CK(cudaMemsetAsync(n_active.p, 0, sizeof(int), stream));
-            k_compact<<<(n_act + 255) / 256, 256, 0, stream>>>(cur, n_act, status.p, nxt, n_active.p);
+            // who is still running?
+            CK(cudaMemsetAsync(split_counts.p, 0, 2 * sizeof(int), stream));
+            k_split<<<(unsigned)((width + 255) / 256), 256, 0, stream>>>(P.status, (int)width, keep_list.p, fin_list.p,
+                                                                        split_counts.p);
             ++launches;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(&n_act, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            int cnt[2] = {0, 0};
+            CK(cudaMemcpyAsync(cnt, split_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
-            std::swap(cur, nxt);
+            if (cnt[0] == (int)width) continue;                 // nobody finished in this launch
+            if (no_repack && cnt[0] > 0 && cur_set < 0) continue;   // debug: finished lanes just idle
+            repack(cnt[0], cnt[1]);
+        }
+        if (width > 0 && cur_set >= 0) {   // max_iter reached between checks: everything left is final
+            CK(cudaMemsetAsync(split_counts.p, 0, 2 * sizeof(int), stream));
+            k_iota<<<(unsigned)((width + 127) / 128), 128, 0, stream>>>(fin_list.p, (int)width);
+            ++launches;
+            repack(0, (int)width);
         }
     }
     k_stats<<<gb, 128, 0, stream>>>(batch, iters.p, status.p, counters.p);

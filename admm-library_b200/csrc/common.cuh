@@ -13,6 +13,14 @@ constexpr int F_K = 0, F_ACL = 18, F_HINV = 54, F_E = 66, F_A = 84, F_B = 120, F
               F_CHAT = 150, FS = 156;
 constexpr int HINV_LD = 4, B_LD = 4;
 
+// packed record of a DECOUPLED model (in-plane states {x,y,vx,vy} = indices {0,1,3,4} with controls
+// {0,1}; cross-track states {z,vz} = {2,5} with control {2}): CW, Yamanaka-Ankersen and every other
+// linearisation about a Kepler orbit have this structure, and so do all of its Riccati matrices.
+// Only the structurally non-zero entries are kept (88 instead of 156 doubles per stage):
+//   Kin[2][4] Kc[2] Aclin[4][4] Aclc[2][2] Hin[2][2] Hc,pad Ein[2][4] Ec[2] Ain[4][4] Ac[2][2] Bin[4][2] Bc[2] c[6] chat[6]
+constexpr int D_KIN = 0, D_KC = 8, D_ACLIN = 10, D_ACLC = 26, D_HIN = 30, D_HC = 34, D_EIN = 36, D_EC = 44,
+              D_AIN = 46, D_AC = 62, D_BIN = 66, D_BC = 74, D_C = 76, D_CHAT = 82, FD = 88;
+
 constexpr int BLK_FREE = 0, BLK_L1 = 1, BLK_L1_BOX = 2, BLK_L2 = 3, BLK_L2_BALL = 4, BLK_BOX = 5,
               BLK_BALL = 6, BLK_POINT = 7, BLK_NONE = 8;
 constexpr int PAR_LAM = 0, PAR_RAD = 1, PAR_LO = 2, PAR_HI = 5;

@@ -280,16 +280,19 @@ __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv,
 // ------------------------------------------------------------------------------------------------
 struct IterParams {
     int N, nb, n;
-    int n_active;
-    const int *active;            // problem indices handled by this launch
+    int n_active;                 // width of the working set (columns 0 .. n_active-1)
+    const int *orig;              // home column of each working-set column (nullptr: identity)
+    size_t hist_ld;               // leading dimension of the history arrays (home layout)
     size_t ld;
     const double *fac;            // shared: [FS*N]; per problem: [FS*N][ld]
     double *fac_rw;               // per-problem factor, writable (refactor)
+    const double *fac_dec;        // packed decoupled records, shared [FD*N] or per problem [FD*N][ld]
+    double *fac_dec_rw;
     const double *rawA, *rawB, *rawc, *rawQ, *rawR;   // raw model for the in-kernel refactor
     int raw_batched;
     const double *s0;             // [6][ld]
     double *z, *u;                // [3*nsplitblk][ld] compact rows of the split blocks
-    double *d;                    // [3N][ld]: d_k after the backward sweep, a_k after the forward
+    double *d;                    // [3N][ld]: d_k of the last backward sweep (k_output rebuilds a_k, x from it)
     const double *q;              // [n] or [n][ld]
     int q_batched;
     const int *bdesc;             // [nb]: type | slot << 8 (slot = compact index of a split block)
@@ -461,7 +464,6 @@ __device__ __forceinline__ void admm_iteration(const IterParams &P, const size_t
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
             a[j] = acc;
-            st_stream(P.d + p + (size_t)(3 * k + j) * ld, acc);
         }
         process_block(3 * k, s[0], s[1], s[2]);
         process_block(3 * k + 1, s[3], s[4], s[5]);
@@ -702,7 +704,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
         }
     }
     const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;   // rows of stage k+2 (loads)
-    double *zw = zp, *uw = up, *dw = dp;                                        // rows of stage k (stores)
+    double *zw = zp, *uw = up;                                                  // rows of stage k (stores)
     auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&s)[6],
                          double (&sn)[6]) {
         double a[3], zo[3], uo[3];
@@ -723,8 +725,6 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             dc[0] = __ldcs(df); dc[1] = __ldcs(df + ld1); dc[2] = __ldcs(df + ld2);
         }
         zf += ld3; uf += ld3; df += ld3;
-        __stcs(dw, a[0]); __stcs(dw + ld1, a[1]); __stcs(dw + ld2, a[2]);
-        dw += ld3;
         {
             const int b = 3 * k + 2;
             double pr[8];
@@ -780,6 +780,381 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decoupled models (in-plane / cross-track).  k_check_decoupled proves the structure on the computed
+// factor (every off-pattern entry of K, Acl, Hinv, E, A, B is exactly zero), pack_decoupled_dev
+// gathers the 88 structurally non-zero entries per stage, admm_iteration_dec is the fast iteration
+// with the zero terms dropped: fma(0, x, acc) == acc, so every accumulator sees the same non-zero
+// terms in the same order as in the oracle and the results stay bit-identical (signed zeros aside).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool in_plane_state(int i) { return i != 2 && i != 5; }
+
+__global__ void k_check_decoupled(int N, int64_t batch, int fac_batched, const double *fac, size_t ld, int *flag)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const size_t ldf = fac_batched ? ld : 1;
+    const double *f = fac + (fac_batched ? (size_t)p : 0);
+    bool bad = false;
+    auto at = [&](int k, int off) { return f[((size_t)k * FS + off) * ldf]; };
+    for (int k = 0; k < N && !bad; ++k) {
+        for (int j = 0; j < 3; ++j) {
+            for (int i = 0; i < 6; ++i) {
+                const bool on = (j < 2) == in_plane_state(i);
+                if (!on) bad |= (at(k, F_K + 6 * j + i) != 0.0) || (at(k, F_E + 6 * j + i) != 0.0) ||
+                                (at(k, F_B + B_LD * i + j) != 0.0);
+            }
+            for (int m = 0; m < 3; ++m)
+                if ((j < 2) != (m < 2)) bad |= at(k, F_HINV + HINV_LD * j + m) != 0.0;
+        }
+        for (int l = 0; l < 6; ++l)
+            for (int i = 0; i < 6; ++i)
+                if (in_plane_state(l) != in_plane_state(i))
+                    bad |= (at(k, F_ACL + 6 * l + i) != 0.0) || (at(k, F_A + 6 * l + i) != 0.0);
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+__device__ __forceinline__ void pack_decoupled_dev(int N, const double *src, size_t lds, double *dst, size_t ldd)
+{
+    const int IP[4] = {0, 1, 3, 4}, CR[2] = {2, 5};
+    for (int k = 0; k < N; ++k) {
+        const double *f = src + (size_t)k * FS * lds;
+        double *o = dst + (size_t)k * FD * ldd;
+        auto S = [&](int off) { return f[(size_t)off * lds]; };
+        auto D = [&](int off, double v) { o[(size_t)off * ldd] = v; };
+        for (int j = 0; j < 2; ++j)
+            for (int c = 0; c < 4; ++c) {
+                D(D_KIN + 4 * j + c, S(F_K + 6 * j + IP[c]));
+                D(D_EIN + 4 * j + c, S(F_E + 6 * j + IP[c]));
+            }
+        for (int c = 0; c < 2; ++c) {
+            D(D_KC + c, S(F_K + 12 + CR[c]));
+            D(D_EC + c, S(F_E + 12 + CR[c]));
+            D(D_BC + c, S(F_B + B_LD * CR[c] + 2));
+        }
+        for (int r = 0; r < 4; ++r) {
+            for (int c = 0; c < 4; ++c) {
+                D(D_ACLIN + 4 * r + c, S(F_ACL + 6 * IP[r] + IP[c]));
+                D(D_AIN + 4 * r + c, S(F_A + 6 * IP[r] + IP[c]));
+            }
+            for (int j = 0; j < 2; ++j) D(D_BIN + 2 * r + j, S(F_B + B_LD * IP[r] + j));
+        }
+        for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 2; ++c) {
+                D(D_ACLC + 2 * r + c, S(F_ACL + 6 * CR[r] + CR[c]));
+                D(D_AC + 2 * r + c, S(F_A + 6 * CR[r] + CR[c]));
+                D(D_HIN + 2 * r + c, S(F_HINV + HINV_LD * r + c));
+            }
+        D(D_HC, S(F_HINV + HINV_LD * 2 + 2));
+        D(D_HC + 1, 0.0);
+        for (int i = 0; i < 6; ++i) {
+            D(D_C + i, S(F_C + i));
+            D(D_CHAT + i, S(F_CHAT + i));
+        }
+    }
+}
+
+__global__ void k_pack_decoupled(int N, int64_t batch, int fac_batched, const double *fac, size_t ld, double *out)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const size_t l = fac_batched ? ld : 1, off = fac_batched ? (size_t)p : 0;
+    pack_decoupled_dev(N, fac + off, l, out + off, l);
+}
+
+// W consecutive doubles of the packed record (W = 2 or 4; offsets are even => 16-byte aligned)
+template <bool FSH, bool FSMEM, int W>
+__device__ __forceinline__ void dec_ld(const FacRef<FSH> &F, int k, int off, double (&r)[W])
+{
+    if (FSH && FSMEM) {
+        const uint32_t a = F.sbase + (uint32_t)(k * FD + off) * 8u;
+        const double2 x = lds128(a);
+        r[0] = x.x; r[1] = x.y;
+        if (W == 4) { const double2 y = lds128(a + 16); r[2] = y.x; r[3] = y.y; }
+    } else if (FSH) {
+        const double2 *q = reinterpret_cast<const double2 *>(F.base + k * FD + off);
+        const double2 x = __ldg(q);
+        r[0] = x.x; r[1] = x.y;
+        if (W == 4) { const double2 y = __ldg(q + 1); r[2] = y.x; r[3] = y.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) r[i] = __ldcs(F.base + ((size_t)k * FD + off + i) * F.ld);
+    }
+}
+
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT>
+__device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const size_t p, const FacRef<FSH> F,
+                                                   const int *bdesc, const uint32_t par_sbase, const double rho,
+                                                   const double sigma, double (&nr)[5])
+{
+    const int N = P.N;
+    const size_t ld = P.ld;
+    const double rinv = 1.0 / rho;
+    const ptrdiff_t ld1 = (ptrdiff_t)ld, ld2 = 2 * (ptrdiff_t)ld, ld3 = 3 * (ptrdiff_t)ld;
+    double *const zp = P.z + p, *const up = P.u + p, *const dp = P.d + p;
+    const double *qp = HAS_Q ? (P.q_batched ? P.q + p : P.q) : nullptr;
+    const size_t qld = P.q_batched ? ld : 1;
+
+    auto load_par = [&](int b, double (&pr)[8]) {
+        if (P.par_batched) {
+            const double *pp = P.par + p + (size_t)(8 * b) * ld;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pr[q] = pp[(size_t)q * ld];
+        } else {
+            const uint32_t a = par_sbase + (uint32_t)b * 64u;
+            const double2 x = lds128(a), y = lds128(a + 16), z = lds128(a + 32), w = lds128(a + 48);
+            pr[0] = x.x; pr[1] = x.y; pr[2] = y.x; pr[3] = y.y; pr[4] = z.x; pr[5] = z.y; pr[6] = w.x; pr[7] = w.y;
+        }
+    };
+    auto rt_terminal = [&](int b, double (&t)[3]) {
+        const int de = bdesc[b];
+        if ((de & 0xff) != BLK_NONE) {
+            const size_t r0 = (size_t)(de >> 8) * 3;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                double uu = __ldcs(up + (r0 + e) * ld);
+                if (ADAPT) uu = uu * sigma;
+                double v = __ldcs(zp + (r0 + e) * ld) - uu;
+                if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
+                t[e] = v;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) t[e] = HAS_Q ? -(qp[(size_t)(3 * b + e) * qld] * rinv) : 0.0;
+        }
+    };
+
+    // ---------------- backward sweep.  g is kept split: gi = (g0,g1,g3,g4) in-plane, gc = (g2,g5) cross-track
+    double giA[4], gcA[2], giB[4], gcB[2];
+    {
+        double t0[3], t1[3];
+        rt_terminal(3 * N, t0);
+        rt_terminal(3 * N + 1, t1);
+        giA[0] = t0[0]; giA[1] = t0[1]; gcA[0] = t0[2]; giA[2] = t1[0]; giA[3] = t1[1]; gcA[1] = t1[2];
+    }
+    double zA[3], uA[3], zB[3], uB[3];
+    {
+        const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
+        zA[0] = __ldcs(z0); zA[1] = __ldcs(z0 + ld1); zA[2] = __ldcs(z0 + ld2);
+        uA[0] = __ldcs(u0); uA[1] = __ldcs(u0 + ld1); uA[2] = __ldcs(u0 + ld2);
+        if (N > 1) {
+            z0 -= ld3; u0 -= ld3;
+            zB[0] = __ldcs(z0); zB[1] = __ldcs(z0 + ld1); zB[2] = __ldcs(z0 + ld2);
+            uB[0] = __ldcs(u0); uB[1] = __ldcs(u0 + ld1); uB[2] = __ldcs(u0 + ld2);
+        }
+    }
+    const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;
+    double *ds = dp + (ptrdiff_t)(N - 1) * ld3;
+    auto bwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], const double (&gi_in)[4],
+                         const double (&gc_in)[2], double (&pi)[4], double (&pc)[2]) {
+        double ra[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            double uu = ADAPT ? uc[e] * sigma : uc[e];
+            double v = zc[e] - uu;
+            if (HAS_Q) v = fma(-qp[(size_t)(9 * k + 6 + e) * qld], rinv, v);
+            ra[e] = v;
+        }
+        if (k >= 2) {
+            zc[0] = __ldcs(zl); zc[1] = __ldcs(zl + ld1); zc[2] = __ldcs(zl + ld2);
+            uc[0] = __ldcs(ul); uc[1] = __ldcs(ul + ld1); uc[2] = __ldcs(ul + ld2);
+        }
+        zl -= ld3; ul -= ld3;
+        double gi[4], gc[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gi[i] = gi_in[i];
+        gc[0] = gc_in[0]; gc[1] = gc_in[1];
+        if (HAS_C) {
+            double c0[4], c1[2];
+            dec_ld<FSH, FSMEM, 4>(F, k, D_CHAT, c0);       // chat[0..3]
+            dec_ld<FSH, FSMEM, 2>(F, k, D_CHAT + 4, c1);   // chat[4..5]
+            gi[0] = gi[0] - c0[0]; gi[1] = gi[1] - c0[1]; gc[0] = gc[0] - c0[2];
+            gi[2] = gi[2] - c0[3]; gi[3] = gi[3] - c1[0]; gc[1] = gc[1] - c1[1];
+        }
+        // rs = -q/rho on the (unsplit) state entries, natural indices 0,1,3,4 | 2,5
+        pi[0] = HAS_Q ? -(qp[(size_t)(9 * k + 0) * qld] * rinv) : 0.0;
+        pi[1] = HAS_Q ? -(qp[(size_t)(9 * k + 1) * qld] * rinv) : 0.0;
+        pi[2] = HAS_Q ? -(qp[(size_t)(9 * k + 3) * qld] * rinv) : 0.0;
+        pi[3] = HAS_Q ? -(qp[(size_t)(9 * k + 4) * qld] * rinv) : 0.0;
+        pc[0] = HAS_Q ? -(qp[(size_t)(9 * k + 2) * qld] * rinv) : 0.0;
+        pc[1] = HAS_Q ? -(qp[(size_t)(9 * k + 5) * qld] * rinv) : 0.0;
+        double dj[3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double h[2], er[4];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_HIN + 2 * j, h);
+            dec_ld<FSH, FSMEM, 4>(F, k, D_EIN + 4 * j, er);
+            double acc = h[0] * ra[0];
+            acc = fma(h[1], ra[1], acc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc = fma(er[i], gi[i], acc);
+            dj[j] = acc;
+        }
+        {
+            double h[2], er[2];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_HC, h);
+            dec_ld<FSH, FSMEM, 2>(F, k, D_EC, er);
+            double acc = h[0] * ra[2];
+            acc = fma(er[0], gc[0], acc);
+            acc = fma(er[1], gc[1], acc);
+            dj[2] = acc;
+        }
+        __stcs(ds, dj[0]); __stcs(ds + ld1, dj[1]); __stcs(ds + ld2, dj[2]);
+        ds -= ld3;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double kr[4];
+            dec_ld<FSH, FSMEM, 4>(F, k, D_KIN + 4 * j, kr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pi[i] = fma(kr[i], ra[j], pi[i]);
+        }
+        {
+            double kr[2];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_KC, kr);
+            pc[0] = fma(kr[0], ra[2], pc[0]);
+            pc[1] = fma(kr[1], ra[2], pc[1]);
+        }
+        // Acl' g: rows l of Acl in ascending natural order 0,1,(2),3,4,(5); in-plane and cross-track
+        // accumulators are disjoint, so the two groups can be walked separately without reordering any sum
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            double ar[4];
+            dec_ld<FSH, FSMEM, 4>(F, k, D_ACLIN + 4 * l, ar);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pi[i] = fma(ar[i], gi[l], pi[i]);
+        }
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            double ar[2];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_ACLC + 2 * l, ar);
+            pc[0] = fma(ar[0], gc[l], pc[0]);
+            pc[1] = fma(ar[1], gc[l], pc[1]);
+        }
+    };
+    {
+        int k = N - 1;
+        for (; k >= 1; k -= 2) {
+            bwd_stage(k, zA, uA, giA, gcA, giB, gcB);
+            bwd_stage(k - 1, zB, uB, giB, gcB, giA, gcA);
+        }
+        if (k == 0) bwd_stage(0, zA, uA, giA, gcA, giB, gcB);
+    }
+
+    // ---------------- forward sweep.  s split the same way: si = (s0,s1,s3,s4), sc = (s2,s5)
+    double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
+    double siA[4], scA[2], siB[4], scB[2];
+    siA[0] = P.s0[p]; siA[1] = P.s0[p + ld]; scA[0] = P.s0[p + 2 * ld];
+    siA[2] = P.s0[p + 3 * ld]; siA[3] = P.s0[p + 4 * ld]; scA[1] = P.s0[p + 5 * ld];
+    double dA[3], dB[3];
+    {
+        zA[0] = __ldcs(zp); zA[1] = __ldcs(zp + ld1); zA[2] = __ldcs(zp + ld2);
+        uA[0] = __ldcs(up); uA[1] = __ldcs(up + ld1); uA[2] = __ldcs(up + ld2);
+        dA[0] = __ldcs(dp); dA[1] = __ldcs(dp + ld1); dA[2] = __ldcs(dp + ld2);
+        if (N > 1) {
+            zB[0] = __ldcs(zp + ld3); zB[1] = __ldcs(zp + ld3 + ld1); zB[2] = __ldcs(zp + ld3 + ld2);
+            uB[0] = __ldcs(up + ld3); uB[1] = __ldcs(up + ld3 + ld1); uB[2] = __ldcs(up + ld3 + ld2);
+            dB[0] = __ldcs(dp + ld3); dB[1] = __ldcs(dp + ld3 + ld1); dB[2] = __ldcs(dp + ld3 + ld2);
+        }
+    }
+    const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;
+    double *zw = zp, *uw = up;
+    auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&si)[4],
+                         const double (&sc)[2], double (&ni)[4], double (&nc)[2]) {
+        double a[3], zo[3], uo[3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double kr[4];
+            dec_ld<FSH, FSMEM, 4>(F, k, D_KIN + 4 * j, kr);
+            double acc = dc[j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc = fma(kr[i], si[i], acc);
+            a[j] = acc;
+        }
+        {
+            double kr[2];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_KC, kr);
+            double acc = dc[2];
+            acc = fma(kr[0], sc[0], acc);
+            acc = fma(kr[1], sc[1], acc);
+            a[2] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { zo[j] = zc[j]; uo[j] = ADAPT ? uc[j] * sigma : uc[j]; }
+        if (k + 2 < N) {
+            zc[0] = __ldcs(zf); zc[1] = __ldcs(zf + ld1); zc[2] = __ldcs(zf + ld2);
+            uc[0] = __ldcs(uf); uc[1] = __ldcs(uf + ld1); uc[2] = __ldcs(uf + ld2);
+            dc[0] = __ldcs(df); dc[1] = __ldcs(df + ld1); dc[2] = __ldcs(df + ld2);
+        }
+        zf += ld3; uf += ld3; df += ld3;
+        {
+            const int b = 3 * k + 2;
+            double pr[8];
+            load_par(b, pr);
+            block_update(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ld, rr,
+                         ss, xx, zz, uu);
+            zw += ld3; uw += ld3;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double ar[4], br[2];
+            dec_ld<FSH, FSMEM, 4>(F, k, D_AIN + 4 * i, ar);
+            dec_ld<FSH, FSMEM, 2>(F, k, D_BIN + 2 * i, br);
+            double acc = ar[0] * si[0];
+            acc = fma(ar[1], si[1], acc);
+            acc = fma(ar[2], si[2], acc);
+            acc = fma(ar[3], si[3], acc);
+            acc = fma(br[0], a[0], acc);
+            acc = fma(br[1], a[1], acc);
+            if (HAS_C) acc = acc + F.base[FSH ? (size_t)(k * FD + D_C + (i < 2 ? i : i + 1)) : ((size_t)k * FD + D_C + (i < 2 ? i : i + 1)) * F.ld];
+            ni[i] = acc;
+        }
+        {
+            double bc[2];
+            dec_ld<FSH, FSMEM, 2>(F, k, D_BC, bc);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double ar[2];
+                dec_ld<FSH, FSMEM, 2>(F, k, D_AC + 2 * i, ar);
+                double acc = ar[0] * sc[0];
+                acc = fma(ar[1], sc[1], acc);
+                acc = fma(bc[i], a[2], acc);
+                if (HAS_C) acc = acc + F.base[FSH ? (size_t)(k * FD + D_C + (i == 0 ? 2 : 5)) : ((size_t)k * FD + D_C + (i == 0 ? 2 : 5)) * F.ld];
+                nc[i] = acc;
+            }
+        }
+    };
+    bool s_in_A = true;
+    {
+        int k = 0;
+        for (; k + 1 < N; k += 2) {
+            fwd_stage(k, zA, uA, dA, siA, scA, siB, scB);
+            fwd_stage(k + 1, zB, uB, dB, siB, scB, siA, scA);
+        }
+        if (k < N) { fwd_stage(k, zA, uA, dA, siA, scA, siB, scB); s_in_A = false; }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int b = 3 * N + t;
+        const int de = bdesc[b];
+        if ((de & 0xff) == BLK_NONE) continue;
+        const size_t r0 = (size_t)(de >> 8) * 3;
+        const double *si = s_in_A ? siA : siB, *sc = s_in_A ? scA : scB;
+        const double xb[3] = {si[2 * t], si[2 * t + 1], sc[t]};       // (s0,s1,s2) or (s3,s4,s5)
+        double zo[3], uo[3], pr[8];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            zo[e] = __ldcs(zp + (r0 + e) * ld);
+            double uv = __ldcs(up + (r0 + e) * ld);
+            uo[e] = ADAPT ? uv * sigma : uv;
+        }
+        load_par(b, pr);
+        block_update(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ld,
+                     up + r0 * ld, ld, rr, ss, xx, zz, uu);
+    }
+    nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous global array into shared memory,
 // completion signalled on an mbarrier: one instruction stages the whole 62 KB factor table.
 // ------------------------------------------------------------------------------------------------
@@ -817,12 +1192,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 // LOWOCC: variant compiled without the 128-register cap, used when the active set is small enough
 // that occupancy does not matter (no spills of the prefetch registers).
 // ------------------------------------------------------------------------------------------------
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, bool FAST, bool LOWOCC>
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int MODE, bool LOWOCC>
 __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __grid_constant__ IterParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *facS = reinterpret_cast<double *>(smem_raw + 16);
-    double *parS = facS + ((FSH && FSMEM) ? (size_t)FS * P.N : 0);
+    constexpr int REC = (MODE == 2) ? FD : FS;                  // doubles per staged factor record
+    const double *fac_src = (MODE == 2) ? P.fac_dec : P.fac;
+    double *parS = facS + ((FSH && FSMEM) ? (size_t)REC * P.N : 0);
     int *bdS = reinterpret_cast<int *>(parS + (P.par_batched ? 0 : 8 * P.nb));
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t fac_sbase = (uint32_t)__cvta_generic_to_shared(facS);
@@ -831,10 +1208,10 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         uint32_t bytes = bd_bytes;
-        if (FSH && FSMEM) bytes += (uint32_t)(FS * P.N * 8);
+        if (FSH && FSMEM) bytes += (uint32_t)(REC * P.N * 8);
         if (!P.par_batched) bytes += (uint32_t)(8 * P.nb * 8);
         mbar_expect_tx(mbar, bytes);
-        if (FSH && FSMEM) bulk_g2s(fac_sbase, P.fac, (uint32_t)(FS * P.N * 8), mbar);
+        if (FSH && FSMEM) bulk_g2s(fac_sbase, fac_src, (uint32_t)(REC * P.N * 8), mbar);
         if (!P.par_batched) bulk_g2s(par_sbase, P.par, (uint32_t)(8 * P.nb * 8), mbar);
         bulk_g2s((uint32_t)__cvta_generic_to_shared(bdS), P.bdesc, bd_bytes, mbar);
     }
@@ -843,11 +1220,11 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n_active) return;
-    const size_t p = (size_t)P.active[t];
+    const size_t p = (size_t)t;       // column of the (densely repacked) working set: always aligned
     if (P.status[p] != ST_RUNNING) return;
 
     FacRef<FSH> F;
-    F.base = FSH ? (FSMEM ? facS : P.fac) : P.fac + p;
+    F.base = FSH ? (FSMEM ? facS : fac_src) : fac_src + p;
     F.ld = P.ld;
     F.sbase = fac_sbase;
 
@@ -859,7 +1236,8 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     for (int cnt = 0; cnt < P.chunk && st == ST_RUNNING; ++cnt) {
         ++it;
         double nr[5];
-        if (FAST) admm_iteration_fast<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
+        if (MODE == 2) admm_iteration_dec<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
+        else if (MODE == 1) admm_iteration_fast<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else admm_iteration<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
         sigma = 1.0;
         r_norm = sqrt(nr[0]);
@@ -868,7 +1246,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
         eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
         eps_dual = fma(P.reltol, rho * sqrt(nr[4]), P.sqrtn_abs);
         if (P.hist) {
-            const size_t h = (size_t)(it - 1) * P.ld + p;
+            const size_t h = (size_t)(it - 1) * P.hist_ld + (P.orig ? (size_t)P.orig[p] : p);   // home column
             P.hist[h] = r_norm;
             P.hist[h + P.hist_stride] = s_norm;
             P.hist[h + 2 * P.hist_stride] = eps_pri;
@@ -891,6 +1269,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
                                              ldr, rho, bdS, P.fac_rw + p, P.ld);
                 atomicAdd(P.refac_count, 1ULL);
                 if (bad) { st = ST_NAN; break; }
+                if (MODE == 2) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
             }
         }
         if (it >= P.max_iter) { st = ST_MAX_ITER; break; }
@@ -906,26 +1285,63 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
-// active-list compaction between launches: keeps the problems still running, counts them.
+// Physical compaction between launches.  A compacted INDEX list leaves warps reading 32 problems that
+// are no longer 256-byte aligned; measured on B200 a shift by ONE problem costs 35 % and a fragmented
+// list up to 4x.  So the still-running problems are physically repacked into a dense, aligned prefix
+// (k_split -> k_gather_cols) and the finished ones are retired to their home columns (k_scatter_cols).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_compact(const int *in, int n_in, const int *status, int *out, int *n_out)
+__global__ void k_split(const int *status, int n, int *keep, int *fin, int *counts)
 {
-    __shared__ int warp_cnt[32];
-    __shared__ int base;
+    __shared__ int wk[32], wf[32];
+    __shared__ int base_k, base_f;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int p = -1, keep = 0;
-    if (t < n_in) { p = in[t]; keep = status[p] == ST_RUNNING; }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[wid] = __popc(m);
+    const bool valid = t < n;
+    const bool k = valid && status[t] == ST_RUNNING, f = valid && !k;
+    const unsigned mk = __ballot_sync(0xffffffffu, k), mf = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) { wk[wid] = __popc(mk); wf[wid] = __popc(mf); }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
-        base = tot ? atomicAdd(n_out, tot) : 0;
+        int tk = 0, tf = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            int c = wk[w]; wk[w] = tk; tk += c;
+            c = wf[w]; wf[w] = tf; tf += c;
+        }
+        base_k = tk ? atomicAdd(counts, tk) : 0;
+        base_f = tf ? atomicAdd(counts + 1, tf) : 0;
     }
     __syncthreads();
-    if (keep) out[base + warp_cnt[wid] + __popc(m & ((1u << lane) - 1))] = p;
+    const unsigned below = (1u << lane) - 1;
+    if (k) keep[base_k + wk[wid] + __popc(mk & below)] = t;
+    if (f) fin[base_f + wf[wid] + __popc(mf & below)] = t;
+}
+
+// out[r][t] = in[r][src[t]], t < n  (rows on blockIdx.y)
+template <typename T>
+__global__ void k_gather_cols(const T *in, size_t ld_in, int rows, const int *src, int n, T *out, size_t ld_out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t c = (size_t)src[t];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) out[(size_t)r * ld_out + t] = in[(size_t)r * ld_in + c];
+}
+
+// home[r][orig[c]] = in[r][c] for the finished columns c = fin[t]
+template <typename T>
+__global__ void k_scatter_cols(const T *in, size_t ld_in, int rows, const int *fin, int n, const int *orig, T *home,
+                               size_t ld_home)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t c = (size_t)fin[t], h = (size_t)orig[c];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) home[(size_t)r * ld_home + h] = in[(size_t)r * ld_in + c];
+}
+
+// orig_new[t] = orig_old ? orig_old[src[t]] : src[t]
+__global__ void k_compose_orig(const int *orig_old, const int *src, int n, int *orig_new)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) orig_new[t] = orig_old ? orig_old[src[t]] : src[t];
 }
 
 __global__ void k_iota(int *a, int n)
@@ -993,7 +1409,12 @@ __global__ void k_output(int N, int64_t batch, size_t ld, const double *fac, con
     for (int k = 0; k < N; ++k) {
         double a[3], sn[6];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) a[j] = d[p + (size_t)(3 * k + j) * ld];
+        for (int j = 0; j < 3; ++j) {      // a_k = d_k + K_k s_k, the forward sweep's operations
+            double acc = d[p + (size_t)(3 * k + j) * ld];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
+            a[j] = acc;
+        }
         emit(3 * k, s[0], s[1], s[2]);
         emit(3 * k + 1, s[3], s[4], s[5]);
         emit(3 * k + 2, a[0], a[1], a[2]);
