@@ -35,7 +35,7 @@ void dense_run(Shard &s, const admmb_opts *op);
 void dense_output(Shard &s, double *xo, double *zo, double *uo);
 void dense_tf32_xupdate(Shard &s);
 int dense_tf32_unit(Shard &s, int n, int64_t batch, size_t ld, const double *M, const double *S, const double *mc,
-                    const double *s0, const double *rt, double *x);
+                    const double *s0, const double *rt, double *x, int split);
 
 // ------------------------------------------------------------------------------------------------
 // one GPU's share of a batch
@@ -639,7 +639,6 @@ void Shard::download(admmb_result *res)
 
 }  // namespace
 
-#include "dense_tf32.cuh"
 #include "dense_impl.cuh"
 
 // ------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "host_util.cuh"
+#include "dense_tf32.cuh"
 
 namespace admmb {
 
@@ -15,6 +16,7 @@ struct DenseState {
     DevBuf<double> x, rt, norms;      // [n][ld], [n][ld], [5][ld]
     DevBuf<int> running;              // [1]
     bool ready = false;
+    Tf32Plan tf32;                    // tensor-core operands and TMA descriptors (precision = tf32)
 };
 
 constexpr int DG_BM = 64, DG_BN = 128, DG_BK = 16;

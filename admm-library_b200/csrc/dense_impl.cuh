@@ -35,6 +35,27 @@ void dense_build_factor(Shard &s, const double *fac_dev, bool has_c, double *M, 
     CK(cudaStreamSynchronize(s.stream));
 }
 
+void dense_tf32_xupdate(Shard &s)
+{
+    s.dense.tf32.gemm(s.stream);
+    ++s.launches;
+}
+
+// unit entry point: X = M RT + S s0 + mc through the tensor-core kernel, FP64 in / FP64 out
+int dense_tf32_unit(Shard &s, int n, int64_t batch, size_t ld, const double *M, const double *S, const double *mc,
+                    const double *s0, const double *rt, double *x, int split)
+{
+    Tf32Plan plan;
+    plan.prepare(n, batch, ld, split, M, S, mc, s0, s.stream);
+    dim3 g((unsigned)((ld + 127) / 128), (unsigned)n);
+    k_tf32_split_rows<<<g, 128, 0, s.stream>>>(n, ld, rt, plan.Bhi.p, split == 3 ? plan.Blo.p : nullptr);
+    plan.gemm(s.stream);
+    k_tf32_to_double<<<g, 128, 0, s.stream>>>(n, ld, plan.X.p, x);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s.stream));
+    return ADMMB_OK;
+}
+
 void dense_prepare(Shard &s, const admmb_opts *)
 {
     DenseState &D = s.dense;
@@ -55,10 +76,18 @@ void dense_run(Shard &s, const admmb_opts *op)
     // factor (shared model, one rho): Riccati factor is already in s.fac
     dense_build_factor(s, s.fac.p, s.has_c, D.M.p, D.S.p, D.mc.p);
     D.ready = true;
+    const bool tf32 = op->precision == ADMMB_PREC_TF32;
+    const int split = getenv("ADMMB_TF32_SINGLE") ? 1 : 3;
     CK(cudaMemsetAsync(D.x.p, 0, sizeof(double) * (size_t)n * s.ld, s.stream));
     k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p,
                                               s.has_q ? s.q.p : nullptr, s.q_batched, D.rt.p);
     ++s.launches;
+    if (tf32) {
+        D.tf32.prepare(n, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
+        dim3 g((unsigned)((s.ld + 127) / 128), (unsigned)n);
+        k_tf32_split_rows<<<g, 128, 0, s.stream>>>(n, s.ld, D.rt.p, D.tf32.Bhi.p, split == 3 ? D.tf32.Blo.p : nullptr);
+        s.launches += 3;
+    }
     DenseStep ds;
     ds.max_iter = op->max_iter;
     ds.reltol = op->reltol;
@@ -69,7 +98,7 @@ void dense_run(Shard &s, const admmb_opts *op)
     int running = 1;
     for (int it = 1; it <= op->max_iter && running > 0; ++it) {
         s.kernel_tic();
-        if (op->precision == ADMMB_PREC_TF32) {
+        if (tf32) {
             dense_tf32_xupdate(s);
         } else {
             k_dense_xupdate_f64<<<gg, 256, 0, s.stream>>>(n, s.batch, s.ld, D.M.p, D.S.p, D.mc.p, s.s0.p, D.rt.p,
@@ -79,9 +108,15 @@ void dense_run(Shard &s, const admmb_opts *op)
         const bool check = (it % chunk) == 0 || it == op->max_iter;
         if (check) CK(cudaMemsetAsync(D.running.p, 0, sizeof(int), s.stream));
         ds.it = it;
-        k_prox_dual_residuals<true><<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched,
-                                                              nullptr, 0.0, op->alpha, D.x.p, s.z.p, s.u.p, nullptr,
-                                                              D.rt.p, s.has_q ? s.q.p : nullptr, s.q_batched, ds);
+        if (tf32)
+            k_prox_dual_residuals<true, true><<<gb, 128, 0, s.stream>>>(
+                nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched, nullptr, 0.0, op->alpha, D.tf32.X.p, s.z.p, s.u.p,
+                nullptr, D.tf32.Bhi.p, D.tf32.split == 3 ? D.tf32.Blo.p : nullptr, D.x.p, s.has_q ? s.q.p : nullptr,
+                s.q_batched, ds);
+        else
+            k_prox_dual_residuals<true, false><<<gb, 128, 0, s.stream>>>(
+                nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched, nullptr, 0.0, op->alpha, D.x.p, s.z.p, s.u.p,
+                nullptr, D.rt.p, nullptr, nullptr, s.has_q ? s.q.p : nullptr, s.q_batched, ds);
         ++s.launches;
         s.kernel_toc();
         CK(cudaGetLastError());

@@ -1575,12 +1575,30 @@ struct DenseStep {
     int *running;              // incremented once per problem still running after this step
 };
 
-template <bool SOLVE>
+// F32: x comes from the TF32 tensor-core GEMM as fp32 and the next right-hand side is written as fp32
+// (hi part = TF32-representable head, optional lo part for the 3xTF32 split); a problem that finishes
+// copies its x column to the FP64 output buffer x_final.
+template <bool SOLVE, bool F32>
 __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const int *bdesc, const double *par,
                                       int par_batched, const double *rinv_arr, double rinv_shared,
-                                      double alpha, const double *x, double *z, double *u, double *norms,
-                                      double *rt_next, const double *q, int q_batched, const DenseStep ds)
+                                      double alpha, const void *xin, double *z, double *u, double *norms,
+                                      void *rt_out, float *rt_lo, double *x_final, const double *q, int q_batched,
+                                      const DenseStep ds)
 {
+    const double *x = F32 ? nullptr : (const double *)xin;
+    const float *x32 = F32 ? (const float *)xin : nullptr;
+    double *rt_next = F32 ? nullptr : (double *)rt_out;
+    float *rt_hi = F32 ? (float *)rt_out : nullptr;
+    auto put_rt = [&](size_t o, double t) {
+        if (F32) {
+            const float f = (float)t;
+            const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
+            rt_hi[o] = h;
+            if (rt_lo) rt_lo[o] = (float)(t - (double)h);
+        } else {
+            rt_next[o] = t;
+        }
+    };
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     if (SOLVE && ds.status[p] != ST_RUNNING) return;
@@ -1591,11 +1609,11 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
     for (int b = 0; b < nb; ++b) {
         const int type = bdesc[b] & 0xff;
         if (type == BLK_NONE) {
-            if (rt_next)
+            if (rt_out)
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
                     const size_t o = (size_t)(3 * b + e) * ld + p;
-                    rt_next[o] = q ? -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv) : 0.0;
+                    put_rt(o, q ? -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv) : 0.0);
                 }
             continue;
         }
@@ -1603,7 +1621,7 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             const size_t o = (size_t)(3 * b + e) * ld + p;
-            xb[e] = ld_stream(x + o);
+            xb[e] = F32 ? (double)x32[o] : ld_stream(x + o);
             zo[e] = ld_stream(z + o);
             double uo = ld_stream(u + o);
             double xh = fma(alpha, xb[e], oma * zo[e]);
@@ -1629,10 +1647,10 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
             uu = fma(un, un, uu);
             st_stream(z + o, zn[e]);
             st_stream(u + o, un);
-            if (rt_next) {
+            if (rt_out) {
                 double t = zn[e] - un;
                 if (q) t = fma(-q[q_batched ? o : (size_t)(3 * b + e)], rinv, t);
-                rt_next[o] = t;
+                put_rt(o, t);
             }
         }
     }
@@ -1659,6 +1677,8 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
         ds.fin[p + 2 * ld] = eps_pri;
         ds.fin[p + 3 * ld] = eps_dual;
         if (st == ST_RUNNING) atomicAdd(ds.running, 1);
+        else if (F32 && x_final)
+            for (int r = 0; r < 3 * nb; ++r) x_final[(size_t)r * ld + p] = (double)x32[(size_t)r * ld + p];
     }
 }
 

@@ -120,8 +120,9 @@ int admmb_k_prox_dual_residuals(admmb_handle h, int32_t N, int64_t batch, const 
         dn.alloc(5 * ld);
         DenseStep ds;
         memset(&ds, 0, sizeof(ds));
-        k_prox_dual_residuals<false><<<(unsigned)((batch + 127) / 128), 128, 0, U.s.stream>>>(
-            nb, batch, ld, bd.p, dpar.p, par_batched, drinv.p, 0.0, alpha, dx.p, dz.p, du.p, dn.p, nullptr, nullptr, 0, ds);
+        k_prox_dual_residuals<false, false><<<(unsigned)((batch + 127) / 128), 128, 0, U.s.stream>>>(
+            nb, batch, ld, bd.p, dpar.p, par_batched, drinv.p, 0.0, alpha, dx.p, dz.p, du.p, dn.p, nullptr, nullptr, nullptr,
+            nullptr, 0, ds);
         CK(cudaGetLastError());
         U.down_rows(dz.p, stg, z, batch, n, ld);
         U.down_rows(du.p, stg, u, batch, n, ld);
@@ -169,8 +170,9 @@ int admmb_k_xupdate_dense(admmb_handle h, int32_t N, int64_t batch, const double
         U.up_rows(ds0, stg, s0, batch, 6, ld);
         U.up_rows(drt, stg, rt, batch, n, ld);
         dx.alloc((size_t)n * ld);
-        if (precision == ADMMB_PREC_TF32) {
-            int rc = dense_tf32_unit(U.s, n, batch, ld, dM.p, dS.p, dmc.p, ds0.p, drt.p, dx.p);
+        if (precision == ADMMB_PREC_TF32 || precision == 2) {
+            // precision 1: 3xTF32 split (what the solver uses); 2: plain single-pass TF32
+            int rc = dense_tf32_unit(U.s, n, batch, ld, dM.p, dS.p, dmc.p, ds0.p, drt.p, dx.p, precision == 2 ? 1 : 3);
             if (rc != ADMMB_OK) return fail(h, rc, "TF32 dense x-update failed");
         } else {
             dim3 gg((unsigned)((batch + DG_BN - 1) / DG_BN), (unsigned)((n + DG_BM - 1) / DG_BM));

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib as L
 
 XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
-PRECISION = {"fp64": 0, "tf32": 1}
+PRECISION = {"fp64": 0, "tf32": 1, "tf32_single": 2}   # tf32 = 3xTF32 split; tf32_single: unit entry point only
 FS = 156  # doubles per stage in a factor record (csrc/common.cuh)
 # name -> (offset, rows, cols, row stride) inside one record
 FAC_LAYOUT = dict(K=(0, 3, 6, 6), Acl=(18, 6, 6, 6), Hinv=(54, 3, 3, 4), E=(66, 3, 6, 6), A=(84, 6, 6, 6),

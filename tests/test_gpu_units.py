@@ -213,3 +213,45 @@ def test_full_size_cfg2_properties(solver, cpu_oracle, P):
     xr, zr, ur, hr = cpu_oracle.solve(sub, opts)
     assert np.array_equal(h["iters"][sl], hr["iters"])
     assert np.array_equal(x[sl], xr) and np.array_equal(z[sl], zr) and np.array_equal(u[sl], ur)
+
+
+# ----------------------------------------------------------------------------- TF32 tensor-core path
+def test_tf32_tcgen05_dense_xupdate_kernel(solver, P):
+    """Row a2' on the tensor cores (tcgen05.mma kind::tf32 + TMA + TMEM).  Stated tolerance: 3xTF32 split
+    operands (what the solver uses) 1e-5 relative to max|x|; single-pass TF32 2e-3 (10-bit mantissa)."""
+    from oracle import admm_ocp as O
+    prob, _ = P.cfg2_cw_batch(batch=1, N=50)
+    N, n = 50, 456
+    wblk, w = O.split_weights(prob["block_type"])
+    d = O.kkt_dense_factor(prob["A"][0], prob["B"][0], None, None, None, 1.0, wblk)
+    rng = np.random.default_rng(3)
+    for B in (100, 1000):
+        s0, rt = rng.standard_normal((B, 6)), w * rng.standard_normal((B, n))
+        ref = rt @ d["M"].T + s0 @ d["S"].T + d["mc"]
+        scale = np.abs(ref).max()
+        x3 = solver.k_xupdate_dense(N, d["M"], d["S"], d["mc"], s0, rt, "tf32")
+        x1 = solver.k_xupdate_dense(N, d["M"], d["S"], d["mc"], s0, rt, "tf32_single")
+        assert np.abs(x3 - ref).max() <= 1e-5 * scale
+        assert 1e-6 * scale < np.abs(x1 - ref).max() <= 2e-3 * scale      # really TF32, not a silent FP64 path
+
+
+@pytest.mark.parametrize("case", ["lqr", "cw"])
+def test_tf32_dense_path_end_to_end(solver, cpu_oracle, P, case):
+    """precision='tf32': a separate, stated precision class (north_star: 1e-4 where TF32 is used).
+    Iteration counts are NOT expected to equal FP64; the converged iterates must agree
+    with the FP64 oracle to 1e-4 relative."""
+    if case == "lqr":
+        prob, opts = P.lqr_tracking(batch=200, N=20, seed=2)
+        opts = dict(opts, max_iter=400, abstol=1e-5, reltol=1e-5)
+    else:
+        prob, opts = P.cfg2_cw_batch(batch=300, N=20, seed=2)
+        opts = dict(opts, max_iter=8000, abstol=1e-5, reltol=1e-5)
+    x, z, u, h = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32"))
+    xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
+    both = (h["status"] == 0) & (hr["status"] == 0)
+    assert both.mean() > 0.7
+    sx = np.abs(xr[both]).max()
+    assert np.abs(x[both] - xr[both]).max() <= 1e-3 * sx       # both are 1e-5-tolerance solutions of the same QP
+    assert np.abs(z[both] - zr[both]).max() <= 1e-3 * sx
+    it_ratio = h["iters"][both].astype(float) / hr["iters"][both]
+    assert 0.5 < np.median(it_ratio) < 2.0
