@@ -7,10 +7,12 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "admm_b200.cu")
+# translation units: the host library + three thirds of the persistent-kernel template variants
+UNITS = ["admm_b200.cu", "iter_smem.cu", "iter_gshared.cu", "iter_pp.cu"]
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libadmm_b200.so")
 
-NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17",
               # explicit fma() only: the operation order written in the kernels is the one executed
               "-fmad=false"]
@@ -32,9 +34,23 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, SRC]
+    obj_dir = os.path.join(OUT_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_unit(name: str) -> str:
+        obj = os.path.join(obj_dir, name.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(HERE, "csrc", name)]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(compile_unit, UNITS))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

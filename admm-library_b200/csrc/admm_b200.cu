@@ -21,6 +21,7 @@
 #include "../../include/admm_b200.h"
 #include "host_util.cuh"
 #include "kernels.cuh"
+#include "iterate_launch_decl.cuh"
 #include "dense.cuh"
 
 using namespace admmb;
@@ -172,8 +173,6 @@ struct Shard {
     void download(admmb_result *res);
     template <bool FSH, bool FSMEM>
     void launch_iterate(const IterParams &P, bool adapt);
-    template <class K1, class K2>
-    void launch_iterate_kernel(K1 kern, K2 kern_lowocc, const IterParams &P, size_t smem);
 };
 
 void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt)
@@ -295,69 +294,14 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     uploaded = true;
 }
 
-// smallest CTA that still puts every active problem on the machine in one wave; otherwise the CTA
-// size with the largest resident capacity.  Returns the resident capacity in *cap_out.
-template <class K>
-static int pick_block(K kern, size_t smem, int num_sms, int n_active, long *cap_out)
-{
-    int bestT = 128;
-    long best_cap = -1;
-    for (int T = 32; T <= 256; T += 32) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem) != cudaSuccess || occ <= 0) continue;
-        long cap = (long)occ * num_sms * T;
-        if ((long)n_active <= cap) { *cap_out = cap; return T; }
-        if (cap > best_cap) { best_cap = cap; bestT = T; }
-    }
-    *cap_out = best_cap;
-    return bestT;
-}
-
-template <class K1, class K2>
-void Shard::launch_iterate_kernel(K1 kern, K2 kern_lowocc, const IterParams &P, size_t smem)
-{
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(kern_lowocc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // the uncapped-register build when it still holds the whole active set in one wave
-    long cap_lo = 0, cap_hi = 0;
-    const int T_lo = pick_block(kern_lowocc, smem, num_sms, P.n_active, &cap_lo);
-    if ((long)P.n_active <= cap_lo) {
-        kern_lowocc<<<(P.n_active + T_lo - 1) / T_lo, T_lo, smem, stream>>>(P);
-    } else {
-        const int T = pick_block(kern, smem, num_sms, P.n_active, &cap_hi);
-        kern<<<(P.n_active + T - 1) / T, T, smem, stream>>>(P);
-    }
-    ++launches;
-    CK(cudaGetLastError());
-}
-
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
-    size_t smem = 16 + ((FSH && FSMEM) ? sizeof(double) * (decoupled ? FD : FS) * N : 0) +
-                  (par_batched ? 0 : sizeof(double) * 8 * nb) +
-                  sizeof(int) * ((nb + 3) / 4) * 4;
-    smem = round_up(smem, 16);
-#define DISPATCH(C, Q, A)                                                                       \
-    do {                                                                                       \
-        if (fast_pattern && decoupled)                                                         \
-            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 2, false>,               \
-                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 2, true>, P, smem);      \
-        else if (fast_pattern)                                                                 \
-            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 1, false>,               \
-                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 1, true>, P, smem);      \
-        else                                                                                   \
-            launch_iterate_kernel(k_admm_iterate<FSH, FSMEM, C, Q, A, 0, false>,               \
-                                  k_admm_iterate<FSH, FSMEM, C, Q, A, 0, true>, P, smem);      \
-    } while (0)
-    if (has_c) {
-        if (has_q) { if (adapt) DISPATCH(true, true, true); else DISPATCH(true, true, false); }
-        else { if (adapt) DISPATCH(true, false, true); else DISPATCH(true, false, false); }
-    } else {
-        if (has_q) { if (adapt) DISPATCH(false, true, true); else DISPATCH(false, true, false); }
-        else { if (adapt) DISPATCH(false, false, true); else DISPATCH(false, false, false); }
-    }
-#undef DISPATCH
+    IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled};
+    if (FSH && FSMEM) launch_iterate_smem(c, P, adapt);
+    else if (FSH) launch_iterate_gshared(c, P, adapt);
+    else launch_iterate_pp(c, P, adapt);
+    ++launches;
 }
 
 // retire the finished columns of the working set to their home columns and move the still-running

@@ -1,0 +1,14 @@
+// iterate_launch_decl.cuh -- declarations of the per-translation-unit launchers (see iterate_launch.cuh)
+#pragma once
+#include "kernels.cuh"
+namespace admmb {
+struct IterLaunchCtx {
+    cudaStream_t stream;
+    int num_sms;
+    int N, nb;
+    bool par_batched, has_c, has_q, fast_pattern, decoupled;
+};
+void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+void launch_iterate_pp(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+}  // namespace admmb

@@ -47,7 +47,7 @@ __device__ __forceinline__ void chol3_solve_dev(const double (&L)[6], double b0,
 // element e of array X is at X[e*ldr] (pointer pre-offset by the problem index); factor entry
 // (k, off) is written to fac[(k*FS+off)*ldf].
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ int riccati_factor_dev(int N, const double *A, const double *B, const double *c,
+static __device__ __noinline__ int riccati_factor_dev(int N, const double *A, const double *B, const double *c,
                                                const double *Q, const double *R, size_t ldr, double rho,
                                                const int *bdesc, double *fac, size_t ldf)
 {
@@ -184,6 +184,7 @@ __device__ __noinline__ int riccati_factor_dev(int N, const double *A, const dou
     return bad;
 }
 
+#ifndef ADMMB_ITERATE_ONLY
 // one thread per factor.  raw_batched: model p at column p of the raw arrays (stride ld), else one
 // contiguous shared model; fac_batched: factor written at column p (stride ld), else contiguous.
 __global__ void k_riccati_factor(int N, int64_t batch, int raw_batched, int fac_batched, const double *A,
@@ -200,6 +201,8 @@ __global__ void k_riccati_factor(int N, int64_t batch, int raw_batched, int fac_
                                  R ? R + off : nullptr, ldr, r, bdesc, fac + offf, ldf);
     if (bad && status) status[p] = ST_NAN;
 }
+
+#endif  // ADMMB_ITERATE_ONLY
 
 // ------------------------------------------------------------------------------------------------
 // Row a3: prox of one 3-block.  par(slot) reads parameter `slot` of this block.
@@ -788,6 +791,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_plane_state(int i) { return i != 2 && i != 5; }
 
+#ifndef ADMMB_ITERATE_ONLY
 __global__ void k_check_decoupled(int N, int64_t batch, int fac_batched, const double *fac, size_t ld, int *flag)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,6 +817,8 @@ __global__ void k_check_decoupled(int N, int64_t batch, int fac_batched, const d
     }
     if (bad) atomicOr(flag, 1);
 }
+
+#endif  // ADMMB_ITERATE_ONLY
 
 __device__ __forceinline__ void pack_decoupled_dev(int N, const double *src, size_t lds, double *dst, size_t ldd)
 {
@@ -854,6 +860,7 @@ __device__ __forceinline__ void pack_decoupled_dev(int N, const double *src, siz
     }
 }
 
+#ifndef ADMMB_ITERATE_ONLY
 __global__ void k_pack_decoupled(int N, int64_t batch, int fac_batched, const double *fac, size_t ld, double *out)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -861,6 +868,8 @@ __global__ void k_pack_decoupled(int N, int64_t batch, int fac_batched, const do
     const size_t l = fac_batched ? ld : 1, off = fac_batched ? (size_t)p : 0;
     pack_decoupled_dev(N, fac + off, l, out + off, l);
 }
+
+#endif  // ADMMB_ITERATE_ONLY
 
 // W consecutive doubles of the packed record (W = 2 or 4; offsets are even => 16-byte aligned)
 template <bool FSH, bool FSMEM, int W>
@@ -1284,6 +1293,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     P.fin[p + 3 * P.ld] = eps_dual;
 }
 
+#ifndef ADMMB_ITERATE_ONLY
 // ------------------------------------------------------------------------------------------------
 // Physical compaction between launches.  A compacted INDEX list leaves warps reading 32 problems that
 // are no longer 256-byte aligned; measured on B200 a shift by ONE problem costs 35 % and a fragmented
@@ -1722,5 +1732,7 @@ __global__ void k_dense_output(int nb, int64_t batch, size_t ld, const int *bdes
         }
     }
 }
+
+#endif  // ADMMB_ITERATE_ONLY
 
 }  // namespace admmb
