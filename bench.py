@@ -139,8 +139,10 @@ def cpu_baseline(prob, opts, sample: int, threads: int = 0) -> dict:
         a = prob.get(k)
         if a is not None and a.shape[0] > 1:
             sub[k] = a[:sample]
+    if threads <= 0:      # every host thread we may use (torchrun exports OMP_NUM_THREADS=1: do not inherit that)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     x, z, u, h = cpu.solve(sub, opts, nthreads=threads)
-    cores = cpu.lib().ocp_num_threads() if threads <= 0 else threads
+    cores = threads
     return {"value": float(h["stats"][1]) / max(h["seconds"], 1e-9), "unit": UNIT, "cores": int(cores),
             "kind": "port", "seconds": h["seconds"], "problem_iterations": int(h["stats"][1]),
             "converged": int(h["stats"][0]),
