@@ -36,7 +36,17 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 3:
     hdr = rows[1]
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    data = [r for r in rows[2:] if len(r) == len(hdr) and r != hdr]
+    # a multi-launch report repeats the table per launch: keep the first one
+    if "Address" in hdr:
+        seen, first = set(), []
+        for r in data:
+            a = r[hdr.index("Address")]
+            if a in seen:
+                break
+            seen.add(a)
+            first.append(r)
+        data = first
     ci = {h: i for i, h in enumerate(hdr)}
     stall = collections.Counter()
     for r in data:

@@ -125,3 +125,52 @@ def test_every_block_type(solver, cpu_oracle, P):
     prob = dict(prob, block_type=bt, block_par=bp)
     got, ref = _both(solver, cpu_oracle, prob, dict(opts, max_iter=250, alpha=1.3, history=1))
     assert_bit_identical(got, ref, "all block types")
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7])
+def test_tiny_and_odd_horizons(solver, cpu_oracle, P, N):
+    """Edge cases of the two-stage prefetch pipeline: horizons shorter than the prefetch distance, odd N."""
+    prob, opts = P.cfg3_lowthrust_soc(batch=37, N=N, seed=N)
+    got, ref = _both(solver, cpu_oracle, prob, dict(opts, rho=1.0, alpha=1.2, max_iter=120, history=1))
+    assert_bit_identical(got, ref, f"N={N}")
+    prob, opts = P.lqr_tracking(batch=19, N=N, seed=N, per_problem=True)
+    got, ref = _both(solver, cpu_oracle, prob, dict(opts, max_iter=60, adapt_rho=1, adapt_every=3, adapt_mu=1.5))
+    assert_bit_identical(got, ref, f"lqr N={N}")
+
+
+def test_coupled_dynamics_take_the_generic_path(solver, cpu_oracle, P):
+    """A model with in-plane / cross-track coupling (not CW-structured) must not use the decoupled kernel."""
+    prob, opts = P.cfg2_cw_batch(batch=70, N=15, seed=6)
+    rng = np.random.default_rng(1)
+    A = prob["A"] + 1e-2 * rng.standard_normal(prob["A"].shape)
+    B = prob["B"] + 1e-2 * rng.standard_normal(prob["B"].shape)
+    got, ref = _both(solver, cpu_oracle, dict(prob, A=A, B=B), dict(opts, max_iter=300, history=1))
+    assert_bit_identical(got, ref, "coupled dynamics")
+
+
+def test_early_exit_repacking_keeps_home_order(solver, cpu_oracle, P):
+    """Problems finish at very different iterations: the working set is repacked many times and every
+    finished problem must land back in its own column."""
+    prob, opts = P.cfg2_cw_batch(batch=700, N=10, seed=12)
+    opts = dict(opts, max_iter=3000, chunk=7, history=0)
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    assert len(np.unique(ref[3]["iters"])) > 100
+    assert_bit_identical(got, ref, "repacking")
+
+
+def test_two_gpus_in_one_process_match_one_gpu(pkg, cpu_oracle, P):
+    """admmb_create with two devices (the MEX deployment): contiguous shards, one worker thread per GPU,
+    results bit-identical to the single-GPU / oracle run."""
+    import ctypes as C
+    try:
+        s2 = pkg.Solver(devices=[0, 1])
+    except pkg.AdmmError:
+        pytest.skip("needs two visible GPUs")
+    prob, opts = P.cfg2_cw_batch(batch=333, N=12, seed=13)
+    opts = dict(opts, max_iter=400)
+    got = s2.solve(prob, opts)
+    assert s2.device_count == 2
+    s2.close()
+    ref = cpu_oracle.solve(prob, opts)
+    assert_bit_identical(got, ref, "two GPUs, one process")
+    assert got[3]["stats"][:3] == [int(v) for v in ref[3]["stats"][:3]]
