@@ -1264,7 +1264,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
         }
         if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; break; }
         if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; break; }
-        if (ADAPT && (it % P.every) == 0 && (P.until <= 0 || it <= P.until)) {
+        if (ADAPT && (it % P.every) == 0 && it < P.max_iter && (P.until <= 0 || it <= P.until)) {
             bool ch = false;
             if (r_norm > P.mu * s_norm) {
                 if (!(rho * P.tau > RHO_MAX)) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }

@@ -79,7 +79,7 @@ function [x, z, u, hist] = admm_ocp(prob, opts)
             end
             if ~(isfinite(r_norm) && isfinite(s_norm)), status = 2; break; end
             if r_norm < eps_pri && s_norm < eps_dual, status = 0; break; end
-            if o.adapt_rho && mod(k, o.adapt_every) == 0 && (o.adapt_until <= 0 || k <= o.adapt_until)
+            if o.adapt_rho && mod(k, o.adapt_every) == 0 && k < o.max_iter && (o.adapt_until <= 0 || k <= o.adapt_until)
                 [rho_new, usc] = adapt_rho(r_norm, s_norm, rho, o.adapt_mu, o.adapt_tau);   % a5
                 if rho_new ~= rho
                     rho = rho_new;  up = up * usc;

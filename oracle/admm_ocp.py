@@ -347,7 +347,7 @@ def admm_solve(prob, opts):
         status[conv] = STATUS_CONVERGED
         status[bad] = STATUS_NAN
         active = a & ~conv & ~bad
-        if adapt and (k % every == 0) and (until <= 0 or k <= until) and active.any():
+        if adapt and (k % every == 0) and k < max_iter and (until <= 0 or k <= until) and active.any():
             rho_new, usc = adapt_rho(r_norm, s_norm, rho, mu, tau)
             ch = active & (rho_new != rho)
             rho = np.where(ch, rho_new, rho)

@@ -508,7 +508,7 @@ int ocp_solve(const ocp_problem *pb, const ocp_opts *op, ocp_result *res, int nt
                 }
                 if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; break; }
                 if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; break; }
-                if (op->adapt_rho && (it % op->adapt_every) == 0 &&
+                if (op->adapt_rho && (it % op->adapt_every) == 0 && it < op->max_iter &&
                     (op->adapt_until <= 0 || it <= op->adapt_until)) {
                     double usc;
                     if (adapt_rho(r_norm, s_norm, op->adapt_mu, op->adapt_tau, inv_tau, &rho, &usc)) {

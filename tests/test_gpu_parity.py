@@ -151,10 +151,10 @@ def test_coupled_dynamics_take_the_generic_path(solver, cpu_oracle, P):
 def test_early_exit_repacking_keeps_home_order(solver, cpu_oracle, P):
     """Problems finish at very different iterations: the working set is repacked many times and every
     finished problem must land back in its own column."""
-    prob, opts = P.cfg2_cw_batch(batch=700, N=10, seed=12)
-    opts = dict(opts, max_iter=3000, chunk=7, history=0)
+    prob, opts = P.cfg2_cw_batch(batch=600, N=20, seed=12)
+    opts = dict(opts, max_iter=2500, chunk=7, history=0)
     got, ref = _both(solver, cpu_oracle, prob, opts)
-    assert len(np.unique(ref[3]["iters"])) > 100
+    assert len(np.unique(ref[3]["iters"])) > 50
     assert_bit_identical(got, ref, "repacking")
 
 
