@@ -29,6 +29,15 @@ constexpr int ST_CONVERGED = 0, ST_MAX_ITER = 1, ST_NAN = 2, ST_RUNNING = -1;
 constexpr int NUM_SMS_B200 = 148;
 constexpr double RHO_MAX = 1.0e6, RHO_MIN = 1.0e-6;   // adaptive rho never leaves this range
 
+// iterate loads / stores of the fast paths.  The two sweeps touch the rows in opposite orders (the backward
+// sweep ends at stage 0, where the forward sweep starts; the forward sweep ends at stage N-1, where the next
+// backward sweep starts), so the most recently touched rows are the next ones needed: cache them in L2
+// (.cg: L2 only, no L1 allocation) instead of streaming them through with evict-first hints.
+#ifndef ADMMB_LD
+#define ADMMB_LD __ldcg
+#define ADMMB_ST __stcg
+#endif
+
 // streaming loads/stores of the iterates: they are touched once per sweep, keep them out of L1
 __device__ __forceinline__ double ld_stream(const double *p)
 {

@@ -555,8 +555,8 @@ __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, d
         xx = fma(xb[e], xb[e], xx);
         zz = fma(zn[e], zn[e], zz);
         uu = fma(un, un, uu);
-        __stcs(zrow + (size_t)e * ld, zn[e]);
-        __stcs(urow + (size_t)e * ld, un);
+        ADMMB_ST(zrow + (size_t)e * ld, zn[e]);
+        ADMMB_ST(urow + (size_t)e * ld, un);
     }
 }
 
@@ -593,9 +593,9 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             const size_t r0 = (size_t)(de >> 8) * 3;
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                double uu = __ldcs(up + (r0 + e) * ld);
+                double uu = ADMMB_LD(up + (r0 + e) * ld);
                 if (ADAPT) uu = uu * sigma;
-                double v = __ldcs(zp + (r0 + e) * ld) - uu;
+                double v = ADMMB_LD(zp + (r0 + e) * ld) - uu;
                 if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
                 t[e] = v;
             }
@@ -616,12 +616,12 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     double zA[3], uA[3], zB[3], uB[3];
     {
         const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
-        zA[0] = __ldcs(z0); zA[1] = __ldcs(z0 + ld1); zA[2] = __ldcs(z0 + ld2);
-        uA[0] = __ldcs(u0); uA[1] = __ldcs(u0 + ld1); uA[2] = __ldcs(u0 + ld2);
+        zA[0] = ADMMB_LD(z0); zA[1] = ADMMB_LD(z0 + ld1); zA[2] = ADMMB_LD(z0 + ld2);
+        uA[0] = ADMMB_LD(u0); uA[1] = ADMMB_LD(u0 + ld1); uA[2] = ADMMB_LD(u0 + ld2);
         if (N > 1) {
             z0 -= ld3; u0 -= ld3;
-            zB[0] = __ldcs(z0); zB[1] = __ldcs(z0 + ld1); zB[2] = __ldcs(z0 + ld2);
-            uB[0] = __ldcs(u0); uB[1] = __ldcs(u0 + ld1); uB[2] = __ldcs(u0 + ld2);
+            zB[0] = ADMMB_LD(z0); zB[1] = ADMMB_LD(z0 + ld1); zB[2] = ADMMB_LD(z0 + ld2);
+            uB[0] = ADMMB_LD(u0); uB[1] = ADMMB_LD(u0 + ld1); uB[2] = ADMMB_LD(u0 + ld2);
         }
     }
     const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;   // rows of stage k-2
@@ -636,8 +636,8 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             ra[e] = v;
         }
         if (k >= 2) {   // refill this buffer with the stage two steps ahead
-            zc[0] = __ldcs(zl); zc[1] = __ldcs(zl + ld1); zc[2] = __ldcs(zl + ld2);
-            uc[0] = __ldcs(ul); uc[1] = __ldcs(ul + ld1); uc[2] = __ldcs(ul + ld2);
+            zc[0] = ADMMB_LD(zl); zc[1] = ADMMB_LD(zl + ld1); zc[2] = ADMMB_LD(zl + ld2);
+            uc[0] = ADMMB_LD(ul); uc[1] = ADMMB_LD(ul + ld1); uc[2] = ADMMB_LD(ul + ld2);
         }
         zl -= ld3; ul -= ld3;
         double gg[6];
@@ -664,7 +664,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             for (int i = 0; i < 6; ++i) acc = fma(er[i], gg[i], acc);
             dj[j] = acc;
         }
-        __stcs(ds, dj[0]); __stcs(ds + ld1, dj[1]); __stcs(ds + ld2, dj[2]);
+        ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]);
         ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -697,13 +697,13 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     for (int i = 0; i < 6; ++i) sA[i] = P.s0[p + (size_t)i * ld];
     double dA[3], dB[3];
     {
-        zA[0] = __ldcs(zp); zA[1] = __ldcs(zp + ld1); zA[2] = __ldcs(zp + ld2);
-        uA[0] = __ldcs(up); uA[1] = __ldcs(up + ld1); uA[2] = __ldcs(up + ld2);
-        dA[0] = __ldcs(dp); dA[1] = __ldcs(dp + ld1); dA[2] = __ldcs(dp + ld2);
+        zA[0] = ADMMB_LD(zp); zA[1] = ADMMB_LD(zp + ld1); zA[2] = ADMMB_LD(zp + ld2);
+        uA[0] = ADMMB_LD(up); uA[1] = ADMMB_LD(up + ld1); uA[2] = ADMMB_LD(up + ld2);
+        dA[0] = ADMMB_LD(dp); dA[1] = ADMMB_LD(dp + ld1); dA[2] = ADMMB_LD(dp + ld2);
         if (N > 1) {
-            zB[0] = __ldcs(zp + ld3); zB[1] = __ldcs(zp + ld3 + ld1); zB[2] = __ldcs(zp + ld3 + ld2);
-            uB[0] = __ldcs(up + ld3); uB[1] = __ldcs(up + ld3 + ld1); uB[2] = __ldcs(up + ld3 + ld2);
-            dB[0] = __ldcs(dp + ld3); dB[1] = __ldcs(dp + ld3 + ld1); dB[2] = __ldcs(dp + ld3 + ld2);
+            zB[0] = ADMMB_LD(zp + ld3); zB[1] = ADMMB_LD(zp + ld3 + ld1); zB[2] = ADMMB_LD(zp + ld3 + ld2);
+            uB[0] = ADMMB_LD(up + ld3); uB[1] = ADMMB_LD(up + ld3 + ld1); uB[2] = ADMMB_LD(up + ld3 + ld2);
+            dB[0] = ADMMB_LD(dp + ld3); dB[1] = ADMMB_LD(dp + ld3 + ld1); dB[2] = ADMMB_LD(dp + ld3 + ld2);
         }
     }
     const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;   // rows of stage k+2 (loads)
@@ -723,9 +723,9 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             uo[j] = ADAPT ? uc[j] * sigma : uc[j];
         }
         if (k + 2 < N) {   // refill this buffer with the stage two steps ahead
-            zc[0] = __ldcs(zf); zc[1] = __ldcs(zf + ld1); zc[2] = __ldcs(zf + ld2);
-            uc[0] = __ldcs(uf); uc[1] = __ldcs(uf + ld1); uc[2] = __ldcs(uf + ld2);
-            dc[0] = __ldcs(df); dc[1] = __ldcs(df + ld1); dc[2] = __ldcs(df + ld2);
+            zc[0] = ADMMB_LD(zf); zc[1] = ADMMB_LD(zf + ld1); zc[2] = ADMMB_LD(zf + ld2);
+            uc[0] = ADMMB_LD(uf); uc[1] = ADMMB_LD(uf + ld1); uc[2] = ADMMB_LD(uf + ld2);
+            dc[0] = ADMMB_LD(df); dc[1] = ADMMB_LD(df + ld1); dc[2] = ADMMB_LD(df + ld2);
         }
         zf += ld3; uf += ld3; df += ld3;
         {
@@ -771,8 +771,8 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
         double zo[3], uo[3], pr[8];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            zo[e] = __ldcs(zp + (r0 + e) * ld);
-            double uv = __ldcs(up + (r0 + e) * ld);
+            zo[e] = ADMMB_LD(zp + (r0 + e) * ld);
+            double uv = ADMMB_LD(up + (r0 + e) * ld);
             uo[e] = ADAPT ? uv * sigma : uv;
         }
         load_par(b, pr);
@@ -887,7 +887,7 @@ __device__ __forceinline__ void dec_ld(const FacRef<FSH> &F, int k, int off, dou
         if (W == 4) { const double2 y = __ldg(q + 1); r[2] = y.x; r[3] = y.y; }
     } else {
 #pragma unroll
-        for (int i = 0; i < W; ++i) r[i] = __ldcs(F.base + ((size_t)k * FD + off + i) * F.ld);
+        for (int i = 0; i < W; ++i) r[i] = ADMMB_LD(F.base + ((size_t)k * FD + off + i) * F.ld);
     }
 }
 
@@ -921,9 +921,9 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             const size_t r0 = (size_t)(de >> 8) * 3;
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                double uu = __ldcs(up + (r0 + e) * ld);
+                double uu = ADMMB_LD(up + (r0 + e) * ld);
                 if (ADAPT) uu = uu * sigma;
-                double v = __ldcs(zp + (r0 + e) * ld) - uu;
+                double v = ADMMB_LD(zp + (r0 + e) * ld) - uu;
                 if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
                 t[e] = v;
             }
@@ -944,12 +944,12 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     double zA[3], uA[3], zB[3], uB[3];
     {
         const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
-        zA[0] = __ldcs(z0); zA[1] = __ldcs(z0 + ld1); zA[2] = __ldcs(z0 + ld2);
-        uA[0] = __ldcs(u0); uA[1] = __ldcs(u0 + ld1); uA[2] = __ldcs(u0 + ld2);
+        zA[0] = ADMMB_LD(z0); zA[1] = ADMMB_LD(z0 + ld1); zA[2] = ADMMB_LD(z0 + ld2);
+        uA[0] = ADMMB_LD(u0); uA[1] = ADMMB_LD(u0 + ld1); uA[2] = ADMMB_LD(u0 + ld2);
         if (N > 1) {
             z0 -= ld3; u0 -= ld3;
-            zB[0] = __ldcs(z0); zB[1] = __ldcs(z0 + ld1); zB[2] = __ldcs(z0 + ld2);
-            uB[0] = __ldcs(u0); uB[1] = __ldcs(u0 + ld1); uB[2] = __ldcs(u0 + ld2);
+            zB[0] = ADMMB_LD(z0); zB[1] = ADMMB_LD(z0 + ld1); zB[2] = ADMMB_LD(z0 + ld2);
+            uB[0] = ADMMB_LD(u0); uB[1] = ADMMB_LD(u0 + ld1); uB[2] = ADMMB_LD(u0 + ld2);
         }
     }
     const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;
@@ -965,8 +965,8 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             ra[e] = v;
         }
         if (k >= 2) {
-            zc[0] = __ldcs(zl); zc[1] = __ldcs(zl + ld1); zc[2] = __ldcs(zl + ld2);
-            uc[0] = __ldcs(ul); uc[1] = __ldcs(ul + ld1); uc[2] = __ldcs(ul + ld2);
+            zc[0] = ADMMB_LD(zl); zc[1] = ADMMB_LD(zl + ld1); zc[2] = ADMMB_LD(zl + ld2);
+            uc[0] = ADMMB_LD(ul); uc[1] = ADMMB_LD(ul + ld1); uc[2] = ADMMB_LD(ul + ld2);
         }
         zl -= ld3; ul -= ld3;
         double gi[4], gc[2];
@@ -1008,7 +1008,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             acc = fma(er[1], gc[1], acc);
             dj[2] = acc;
         }
-        __stcs(ds, dj[0]); __stcs(ds + ld1, dj[1]); __stcs(ds + ld2, dj[2]);
+        ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]);
         ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1056,13 +1056,13 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     siA[2] = P.s0[p + 3 * ld]; siA[3] = P.s0[p + 4 * ld]; scA[1] = P.s0[p + 5 * ld];
     double dA[3], dB[3];
     {
-        zA[0] = __ldcs(zp); zA[1] = __ldcs(zp + ld1); zA[2] = __ldcs(zp + ld2);
-        uA[0] = __ldcs(up); uA[1] = __ldcs(up + ld1); uA[2] = __ldcs(up + ld2);
-        dA[0] = __ldcs(dp); dA[1] = __ldcs(dp + ld1); dA[2] = __ldcs(dp + ld2);
+        zA[0] = ADMMB_LD(zp); zA[1] = ADMMB_LD(zp + ld1); zA[2] = ADMMB_LD(zp + ld2);
+        uA[0] = ADMMB_LD(up); uA[1] = ADMMB_LD(up + ld1); uA[2] = ADMMB_LD(up + ld2);
+        dA[0] = ADMMB_LD(dp); dA[1] = ADMMB_LD(dp + ld1); dA[2] = ADMMB_LD(dp + ld2);
         if (N > 1) {
-            zB[0] = __ldcs(zp + ld3); zB[1] = __ldcs(zp + ld3 + ld1); zB[2] = __ldcs(zp + ld3 + ld2);
-            uB[0] = __ldcs(up + ld3); uB[1] = __ldcs(up + ld3 + ld1); uB[2] = __ldcs(up + ld3 + ld2);
-            dB[0] = __ldcs(dp + ld3); dB[1] = __ldcs(dp + ld3 + ld1); dB[2] = __ldcs(dp + ld3 + ld2);
+            zB[0] = ADMMB_LD(zp + ld3); zB[1] = ADMMB_LD(zp + ld3 + ld1); zB[2] = ADMMB_LD(zp + ld3 + ld2);
+            uB[0] = ADMMB_LD(up + ld3); uB[1] = ADMMB_LD(up + ld3 + ld1); uB[2] = ADMMB_LD(up + ld3 + ld2);
+            dB[0] = ADMMB_LD(dp + ld3); dB[1] = ADMMB_LD(dp + ld3 + ld1); dB[2] = ADMMB_LD(dp + ld3 + ld2);
         }
     }
     const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;
@@ -1090,9 +1090,9 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
 #pragma unroll
         for (int j = 0; j < 3; ++j) { zo[j] = zc[j]; uo[j] = ADAPT ? uc[j] * sigma : uc[j]; }
         if (k + 2 < N) {
-            zc[0] = __ldcs(zf); zc[1] = __ldcs(zf + ld1); zc[2] = __ldcs(zf + ld2);
-            uc[0] = __ldcs(uf); uc[1] = __ldcs(uf + ld1); uc[2] = __ldcs(uf + ld2);
-            dc[0] = __ldcs(df); dc[1] = __ldcs(df + ld1); dc[2] = __ldcs(df + ld2);
+            zc[0] = ADMMB_LD(zf); zc[1] = ADMMB_LD(zf + ld1); zc[2] = ADMMB_LD(zf + ld2);
+            uc[0] = ADMMB_LD(uf); uc[1] = ADMMB_LD(uf + ld1); uc[2] = ADMMB_LD(uf + ld2);
+            dc[0] = ADMMB_LD(df); dc[1] = ADMMB_LD(df + ld1); dc[2] = ADMMB_LD(df + ld2);
         }
         zf += ld3; uf += ld3; df += ld3;
         {
@@ -1152,8 +1152,8 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
         double zo[3], uo[3], pr[8];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            zo[e] = __ldcs(zp + (r0 + e) * ld);
-            double uv = __ldcs(up + (r0 + e) * ld);
+            zo[e] = ADMMB_LD(zp + (r0 + e) * ld);
+            double uv = ADMMB_LD(up + (r0 + e) * ld);
             uo[e] = ADAPT ? uv * sigma : uv;
         }
         load_par(b, pr);
