@@ -465,8 +465,12 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         ld_cur = ld;
         const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
 
+        // launches get longer once few problems finish per launch: the host round trip (split, count
+        // read-back, repack) then costs relatively less and nothing is lost in early-exit granularity
+        const int chunk_max = op->chunk > 0 ? op->chunk : 400;
         int done_iters = 0;
         while (width > 0 && done_iters < op->max_iter) {
+            P.chunk = chunk;
             P.ld = ld_cur;
             P.n_active = (int)width;
             P.orig = cur_set < 0 ? nullptr : orig[cur_set].p;
@@ -500,6 +504,14 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             int cnt[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt, split_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
+            if (op->chunk <= 0) {
+                // adapt the launch length: finished problems idle until the launch ends, so aim at <= 1 % of the
+                // working set finishing per launch, estimated from the finish rate of the launch just done
+                const int prev = chunk;
+                if (cnt[1] == 0) chunk = std::min(chunk * 2, chunk_max);
+                else chunk = (int)std::min<long long>(chunk_max, std::max<long long>(50, (long long)width * prev / (100LL * cnt[1])));
+                if (adapt && P.every > 0 && chunk > P.every) chunk = (chunk / P.every) * P.every;
+            }
             if (cnt[0] == (int)width) continue;                 // nobody finished in this launch
             if (no_repack && cnt[0] > 0 && cur_set < 0) continue;   // debug: finished lanes just idle
             repack(cnt[0], cnt[1]);

@@ -2,6 +2,7 @@
 // variants; they are instantiated in three translation units (iter_smem.cu, iter_gshared.cu, iter_pp.cu),
 // compiled in parallel, so that a rebuild takes about a minute instead of four.
 #pragma once
+#include <cstdlib>
 #include "host_util.cuh"
 #define ADMMB_ITERATE_ONLY
 #include "kernels.cuh"
@@ -9,36 +10,65 @@
 
 namespace admmb {
 
-// smallest CTA that still puts every active problem on the machine in one wave; otherwise the CTA
-// size with the largest resident capacity.  Returns the resident capacity in *cap_out.
+// Resident capacity of one kernel variant for CTA sizes 32..256, queried once and cached: the launch
+// loop runs hundreds of times per solve with the GPU idle while the host decides.
+struct OccTable {
+    const void *kern = nullptr;
+    size_t smem = 0;
+    int num_sms = 0;
+    long cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 template <class K>
-static int pick_block(K kern, size_t smem, int num_sms, int n_active, long *cap_out)
+static const OccTable &occ_table(K kern, size_t smem, int num_sms)
 {
-    int bestT = 128;
-    long best_cap = -1;
-    for (int T = 32; T <= 256; T += 32) {
+    static thread_local OccTable cache[32];
+    static thread_local int used = 0;
+    // the dynamic-smem limit is per-function state: it must cover the largest request made so far
+    size_t attr = 0;
+    const OccTable *hit = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].kern == (const void *)kern) {
+            attr = attr > cache[i].smem ? attr : cache[i].smem;
+            if (cache[i].smem == smem && cache[i].num_sms == num_sms) hit = &cache[i];
+        }
+    if (hit) return *hit;
+    if (smem > attr) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (used == 32) used = 0;   // tiny cache: start over (re-queries, never wrong: attr is re-derived from live entries)
+    OccTable &t = cache[used++];
+    t.kern = (const void *)kern; t.smem = smem; t.num_sms = num_sms;
+    for (int i = 0; i < 8; ++i) {
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem) != cudaSuccess || occ <= 0) continue;
-        long cap = (long)occ * num_sms * T;
-        if ((long)n_active <= cap) { *cap_out = cap; return T; }
-        if (cap > best_cap) { best_cap = cap; bestT = T; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (i + 1), smem) != cudaSuccess) occ = 0;
+        t.cap[i] = (long)occ * num_sms * 32 * (i + 1);
     }
-    *cap_out = best_cap;
-    return bestT;
+    return t;
+}
+
+// smallest CTA that still puts every active problem on the machine in one wave; otherwise the CTA
+// size with the largest resident capacity.
+static int pick_block(const OccTable &t, int n_active, bool *one_wave)
+{
+    int best = 3;
+    static const int min_i = getenv("ADMMB_MIN_BLOCK") ? atoi(getenv("ADMMB_MIN_BLOCK")) / 32 - 1 : 0;   // tuning knob
+    for (int i = min_i; i < 8; ++i) {
+        if (t.cap[i] >= (long)n_active) { *one_wave = true; return 32 * (i + 1); }
+        if (t.cap[i] > t.cap[best]) best = i;
+    }
+    *one_wave = false;
+    return 32 * (best + 1);
 }
 
 template <class K1, class K2>
 static void launch_iterate_kernel(const IterLaunchCtx &c, K1 kern, K2 kern_lowocc, const IterParams &P, size_t smem)
 {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(kern_lowocc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the uncapped-register build when it still holds the whole active set in one wave
-    long cap_lo = 0, cap_hi = 0;
-    const int T_lo = pick_block(kern_lowocc, smem, c.num_sms, P.n_active, &cap_lo);
-    if ((long)P.n_active <= cap_lo) {
+    bool one_wave = false;
+    const int T_lo = pick_block(occ_table(kern_lowocc, smem, c.num_sms), P.n_active, &one_wave);
+    if (one_wave) {
         kern_lowocc<<<(P.n_active + T_lo - 1) / T_lo, T_lo, smem, c.stream>>>(P);
     } else {
-        const int T = pick_block(kern, smem, c.num_sms, P.n_active, &cap_hi);
+        const int T = pick_block(occ_table(kern, smem, c.num_sms), P.n_active, &one_wave);
         kern<<<(P.n_active + T - 1) / T, T, smem, c.stream>>>(P);
     }
     CK(cudaGetLastError());

@@ -206,7 +206,30 @@ __global__ void k_riccati_factor(int N, int64_t batch, int raw_batched, int fac_
 
 // ------------------------------------------------------------------------------------------------
 // Row a3: prox of one 3-block.  par(slot) reads parameter `slot` of this block.
+// Every data-dependent choice is a select (setp + selp), never a branch: neighbouring problems saturate,
+// shrink to zero or stay interior independently, and divergent branches here cost a latency-bound warp
+// 33 % of its iteration time (measured: 1.71 ms -> 2.27 ms per 50 iterations once the lanes' active sets
+// differ).  The selected values are exactly the oracle's; unselected ones (e.g. 0/0) are discarded.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sel_gt(double a, double b, double x, double y)   // (a > b) ? x : y
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %3, %4, p;\n\t}"
+        : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+    return r;
+}
+__device__ __forceinline__ double sel_lt(double a, double b, double x, double y)   // (a < b) ? x : y
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %3, %4, p;\n\t}"
+        : "=d"(r) : "d"(a), "d"(b), "d"(x), "d"(y));
+    return r;
+}
+__device__ __forceinline__ double clip_sel(double t, double lo, double hi)          // t < lo ? lo : (t > hi ? hi : t)
+{
+    return sel_lt(t, lo, lo, sel_gt(t, hi, hi, t));
+}
+
 template <class ParFn>
 __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv, const double (&v)[3],
                                                double (&z)[3])
@@ -217,14 +240,11 @@ __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv,
         const double kap = par(PAR_LAM) * rinv;
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            // soft threshold without branches: |v| - kap equals v - kap (v > kap) and -(v + kap)
-            // (v < -kap) bit for bit, so this is the oracle's three-way form as two selects
+            // |v| - kap equals v - kap (v > kap) and -(v + kap) (v < -kap) bit for bit, so this is the
+            // oracle's three-way soft threshold
             const double m = fabs(v[e]) - kap;
-            double t = m > 0.0 ? copysign(m, v[e]) : 0.0;
-            if (type == BLK_L1_BOX) {
-                double lo = par(PAR_LO + e), hi = par(PAR_HI + e);
-                t = t < lo ? lo : (t > hi ? hi : t);
-            }
+            double t = sel_gt(m, 0.0, copysign(m, v[e]), 0.0);
+            if (type == BLK_L1_BOX) t = clip_sel(t, par(PAR_LO + e), par(PAR_HI + e));
             z[e] = t;
         }
         break;
@@ -235,38 +255,29 @@ __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv,
         double sq = v[0] * v[0];
         sq = fma(v[1], v[1], sq);
         sq = fma(v[2], v[2], sq);
-        double nrm = sqrt(sq);
-        if (nrm > kap) {
-            double mag = nrm - kap;
-            if (type == BLK_L2_BALL) { double rad = par(PAR_RAD); if (mag > rad) mag = rad; }
-            double sc = mag / nrm;
+        const double nrm = sqrt(sq);
+        double mag = nrm - kap;
+        if (type == BLK_L2_BALL) { const double rad = par(PAR_RAD); mag = sel_gt(mag, rad, rad, mag); }
+        const double sc = mag / nrm;                       // discarded when nrm <= kap (incl. 0/0)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) z[e] = sc * v[e];
-        } else {
-            z[0] = 0.0; z[1] = 0.0; z[2] = 0.0;
-        }
+        for (int e = 0; e < 3; ++e) z[e] = sel_gt(nrm, kap, sc * v[e], 0.0);
         break;
     }
     case BLK_BOX:
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            double lo = par(PAR_LO + e), hi = par(PAR_HI + e);
-            z[e] = v[e] < lo ? lo : (v[e] > hi ? hi : v[e]);
-        }
+        for (int e = 0; e < 3; ++e) z[e] = clip_sel(v[e], par(PAR_LO + e), par(PAR_HI + e));
         break;
     case BLK_BALL: {
-        double c0 = par(PAR_LO), c1 = par(PAR_LO + 1), c2 = par(PAR_LO + 2), rad = par(PAR_RAD);
-        double w0 = v[0] - c0, w1 = v[1] - c1, w2 = v[2] - c2;
+        const double c0 = par(PAR_LO), c1 = par(PAR_LO + 1), c2 = par(PAR_LO + 2), rad = par(PAR_RAD);
+        const double w0 = v[0] - c0, w1 = v[1] - c1, w2 = v[2] - c2;
         double sq = w0 * w0;
         sq = fma(w1, w1, sq);
         sq = fma(w2, w2, sq);
-        double nrm = sqrt(sq);
-        if (nrm > rad) {
-            double sc = rad / nrm;
-            z[0] = fma(sc, w0, c0); z[1] = fma(sc, w1, c1); z[2] = fma(sc, w2, c2);
-        } else {
-            z[0] = v[0]; z[1] = v[1]; z[2] = v[2];
-        }
+        const double nrm = sqrt(sq);
+        const double sc = rad / nrm;                       // discarded when nrm <= rad
+        z[0] = sel_gt(nrm, rad, fma(sc, w0, c0), v[0]);
+        z[1] = sel_gt(nrm, rad, fma(sc, w1, c1), v[1]);
+        z[2] = sel_gt(nrm, rad, fma(sc, w2, c2), v[2]);
         break;
     }
     case BLK_POINT:
@@ -891,7 +902,9 @@ __device__ __forceinline__ void dec_ld(const FacRef<FSH> &F, int k, int off, dou
     }
 }
 
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT>
+// PD = prefetch distance in stages (even): 2 under the 128-register cap, 4 in the uncapped build, where a
+// lone warp per sub-partition has nothing else to hide the global-load latency behind.
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int PD>
 __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const size_t p, const FacRef<FSH> F,
                                                    const int *bdesc, const uint32_t par_sbase, const double rho,
                                                    const double sigma, double (&nr)[5])
@@ -941,18 +954,15 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
         rt_terminal(3 * N + 1, t1);
         giA[0] = t0[0]; giA[1] = t0[1]; gcA[0] = t0[2]; giA[2] = t1[0]; giA[3] = t1[1]; gcA[1] = t1[2];
     }
-    double zA[3], uA[3], zB[3], uB[3];
-    {
-        const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
-        zA[0] = ADMMB_LD(z0); zA[1] = ADMMB_LD(z0 + ld1); zA[2] = ADMMB_LD(z0 + ld2);
-        uA[0] = ADMMB_LD(u0); uA[1] = ADMMB_LD(u0 + ld1); uA[2] = ADMMB_LD(u0 + ld2);
-        if (N > 1) {
-            z0 -= ld3; u0 -= ld3;
-            zB[0] = ADMMB_LD(z0); zB[1] = ADMMB_LD(z0 + ld1); zB[2] = ADMMB_LD(z0 + ld2);
-            uB[0] = ADMMB_LD(u0); uB[1] = ADMMB_LD(u0 + ld1); uB[2] = ADMMB_LD(u0 + ld2);
+    double zb[PD][3], ub[PD][3];                       // slot u holds stage (top - u) of the current group
+#pragma unroll
+    for (int t = 0; t < PD; ++t)
+        if (N - 1 - t >= 0) {
+            const double *z0 = zp + (ptrdiff_t)(N - 1 - t) * ld3, *u0 = up + (ptrdiff_t)(N - 1 - t) * ld3;
+            zb[t][0] = ADMMB_LD(z0); zb[t][1] = ADMMB_LD(z0 + ld1); zb[t][2] = ADMMB_LD(z0 + ld2);
+            ub[t][0] = ADMMB_LD(u0); ub[t][1] = ADMMB_LD(u0 + ld1); ub[t][2] = ADMMB_LD(u0 + ld2);
         }
-    }
-    const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;
+    const double *zl = zp + (ptrdiff_t)(N - 1 - PD) * ld3, *ul = up + (ptrdiff_t)(N - 1 - PD) * ld3;   // stage k-PD
     double *ds = dp + (ptrdiff_t)(N - 1) * ld3;
     auto bwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], const double (&gi_in)[4],
                          const double (&gc_in)[2], double (&pi)[4], double (&pc)[2]) {
@@ -964,7 +974,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             if (HAS_Q) v = fma(-qp[(size_t)(9 * k + 6 + e) * qld], rinv, v);
             ra[e] = v;
         }
-        if (k >= 2) {
+        if (k >= PD) {   // refill this slot with the stage PD steps ahead
             zc[0] = ADMMB_LD(zl); zc[1] = ADMMB_LD(zl + ld1); zc[2] = ADMMB_LD(zl + ld2);
             uc[0] = ADMMB_LD(ul); uc[1] = ADMMB_LD(ul + ld1); uc[2] = ADMMB_LD(ul + ld2);
         }
@@ -1040,13 +1050,27 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             pc[1] = fma(ar[1], gc[l], pc[1]);
         }
     };
+    // PD == 2 (register-capped build): one guarded copy of the stage body per slot keeps the code small and the
+    // register allocator out of spills.  PD == 4 (uncapped build, latency-bound warps): an unguarded main loop
+    // lets the scheduler overlap neighbouring stages; the short remainder is guarded.
     {
         int k = N - 1;
-        for (; k >= 1; k -= 2) {
-            bwd_stage(k, zA, uA, giA, gcA, giB, gcB);
-            bwd_stage(k - 1, zB, uB, giB, gcB, giA, gcA);
+        if (PD > 2) {
+            for (; k >= PD - 1; k -= PD) {
+#pragma unroll
+                for (int t = 0; t < PD; t += 2) {
+                    bwd_stage(k - t, zb[t], ub[t], giA, gcA, giB, gcB);
+                    bwd_stage(k - t - 1, zb[t + 1], ub[t + 1], giB, gcB, giA, gcA);
+                }
+            }
         }
-        if (k == 0) bwd_stage(0, zA, uA, giA, gcA, giB, gcB);
+        for (; k >= 0; k -= PD) {
+#pragma unroll
+            for (int t = 0; t < PD; t += 2) {
+                if (k - t >= 0) bwd_stage(k - t, zb[t], ub[t], giA, gcA, giB, gcB);
+                if (k - t - 1 >= 0) bwd_stage(k - t - 1, zb[t + 1], ub[t + 1], giB, gcB, giA, gcA);
+            }
+        }
     }
 
     // ---------------- forward sweep.  s split the same way: si = (s0,s1,s3,s4), sc = (s2,s5)
@@ -1054,18 +1078,16 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     double siA[4], scA[2], siB[4], scB[2];
     siA[0] = P.s0[p]; siA[1] = P.s0[p + ld]; scA[0] = P.s0[p + 2 * ld];
     siA[2] = P.s0[p + 3 * ld]; siA[3] = P.s0[p + 4 * ld]; scA[1] = P.s0[p + 5 * ld];
-    double dA[3], dB[3];
-    {
-        zA[0] = ADMMB_LD(zp); zA[1] = ADMMB_LD(zp + ld1); zA[2] = ADMMB_LD(zp + ld2);
-        uA[0] = ADMMB_LD(up); uA[1] = ADMMB_LD(up + ld1); uA[2] = ADMMB_LD(up + ld2);
-        dA[0] = ADMMB_LD(dp); dA[1] = ADMMB_LD(dp + ld1); dA[2] = ADMMB_LD(dp + ld2);
-        if (N > 1) {
-            zB[0] = ADMMB_LD(zp + ld3); zB[1] = ADMMB_LD(zp + ld3 + ld1); zB[2] = ADMMB_LD(zp + ld3 + ld2);
-            uB[0] = ADMMB_LD(up + ld3); uB[1] = ADMMB_LD(up + ld3 + ld1); uB[2] = ADMMB_LD(up + ld3 + ld2);
-            dB[0] = ADMMB_LD(dp + ld3); dB[1] = ADMMB_LD(dp + ld3 + ld1); dB[2] = ADMMB_LD(dp + ld3 + ld2);
+    double db[PD][3];
+#pragma unroll
+    for (int t = 0; t < PD; ++t)
+        if (t < N) {
+            const double *z0 = zp + (ptrdiff_t)t * ld3, *u0 = up + (ptrdiff_t)t * ld3, *d0 = dp + (ptrdiff_t)t * ld3;
+            zb[t][0] = ADMMB_LD(z0); zb[t][1] = ADMMB_LD(z0 + ld1); zb[t][2] = ADMMB_LD(z0 + ld2);
+            ub[t][0] = ADMMB_LD(u0); ub[t][1] = ADMMB_LD(u0 + ld1); ub[t][2] = ADMMB_LD(u0 + ld2);
+            db[t][0] = ADMMB_LD(d0); db[t][1] = ADMMB_LD(d0 + ld1); db[t][2] = ADMMB_LD(d0 + ld2);
         }
-    }
-    const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;
+    const double *zf = zp + PD * ld3, *uf = up + PD * ld3, *df = dp + PD * ld3;   // stage k+PD
     double *zw = zp, *uw = up;
     auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&si)[4],
                          const double (&sc)[2], double (&ni)[4], double (&nc)[2]) {
@@ -1089,7 +1111,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) { zo[j] = zc[j]; uo[j] = ADAPT ? uc[j] * sigma : uc[j]; }
-        if (k + 2 < N) {
+        if (k + PD < N) {
             zc[0] = ADMMB_LD(zf); zc[1] = ADMMB_LD(zf + ld1); zc[2] = ADMMB_LD(zf + ld2);
             uc[0] = ADMMB_LD(uf); uc[1] = ADMMB_LD(uf + ld1); uc[2] = ADMMB_LD(uf + ld2);
             dc[0] = ADMMB_LD(df); dc[1] = ADMMB_LD(df + ld1); dc[2] = ADMMB_LD(df + ld2);
@@ -1132,14 +1154,25 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             }
         }
     };
-    bool s_in_A = true;
+    const bool s_in_A = (N & 1) == 0;                   // every stage flips the s ping-pong
     {
         int k = 0;
-        for (; k + 1 < N; k += 2) {
-            fwd_stage(k, zA, uA, dA, siA, scA, siB, scB);
-            fwd_stage(k + 1, zB, uB, dB, siB, scB, siA, scA);
+        if (PD > 2) {
+            for (; k + PD <= N; k += PD) {
+#pragma unroll
+                for (int t = 0; t < PD; t += 2) {
+                    fwd_stage(k + t, zb[t], ub[t], db[t], siA, scA, siB, scB);
+                    fwd_stage(k + t + 1, zb[t + 1], ub[t + 1], db[t + 1], siB, scB, siA, scA);
+                }
+            }
         }
-        if (k < N) { fwd_stage(k, zA, uA, dA, siA, scA, siB, scB); s_in_A = false; }
+        for (; k < N; k += PD) {
+#pragma unroll
+            for (int t = 0; t < PD; t += 2) {
+                if (k + t < N) fwd_stage(k + t, zb[t], ub[t], db[t], siA, scA, siB, scB);
+                if (k + t + 1 < N) fwd_stage(k + t + 1, zb[t + 1], ub[t + 1], db[t + 1], siB, scB, siA, scA);
+            }
+        }
     }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -1245,7 +1278,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     for (int cnt = 0; cnt < P.chunk && st == ST_RUNNING; ++cnt) {
         ++it;
         double nr[5];
-        if (MODE == 2) admm_iteration_dec<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
+        if (MODE == 2) admm_iteration_dec<FSH, FSMEM, HAS_C, HAS_Q, ADAPT, (LOWOCC ? 4 : 2)>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else if (MODE == 1) admm_iteration_fast<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else admm_iteration<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
         sigma = 1.0;
