@@ -71,7 +71,8 @@ __device__ __forceinline__ void tg_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// grid = (ceil(ld / 128), Mpad / 128); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// grid = (Mpad / 128, ceil(ld / 128)): the M-tiles that share one B (right-hand-side) tile are neighbours in launch
+// order, so they run together and B is fetched from DRAM once, then from L2.  192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
 // warps 2..5 epilogue (TMEM lane quarter = warp % 4).
 template <int SPLIT>   // 1: plain TF32; 3: hi/lo split operands (Ah*Bh + Ah*Bl + Al*Bh)
 __global__ void __launch_bounds__(192, 1)
@@ -90,7 +91,7 @@ k_dense_xupdate_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const uint32_t tmem_full = bars + 8u * (2 * TG_STAGES);
     const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+    const int m0 = blockIdx.x * TG_BM, n0 = blockIdx.y * TG_BN;
     const int KB = (kpad + TG_BK - 1) / TG_BK;
 
     if (threadIdx.x == 0) {
@@ -329,7 +330,7 @@ struct Tf32Plan {
     float *dbg = nullptr;
     void gemm(cudaStream_t st)
     {
-        dim3 grid((unsigned)((ld + TG_BN - 1) / TG_BN), (unsigned)(mpad / TG_BM));
+        dim3 grid((unsigned)(mpad / TG_BM), (unsigned)((ld + TG_BN - 1) / TG_BN));
         if (split == 3) {
             CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
             k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, X.p, dbg);
