@@ -174,3 +174,60 @@ def test_two_gpus_in_one_process_match_one_gpu(pkg, cpu_oracle, P):
     ref = cpu_oracle.solve(prob, opts)
     assert_bit_identical(got, ref, "two GPUs, one process")
     assert got[3]["stats"][:3] == [int(v) for v in ref[3]["stats"][:3]]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_problem_shapes(solver, cpu_oracle, P, seed):
+    """Randomised sweep over what the boundary accepts: horizon, batch, block pattern (any type on any
+    block, incl. state blocks), shared / per-problem models, parameters and linear cost, quadratic cost,
+    affine dynamics, relaxation, adaptive rho, warm start.  Every combination must be bit-identical."""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(1, 13))
+    B = int(rng.integers(1, 90))
+    n, nb = 9 * N + 6, 3 * N + 2
+    per_problem = bool(rng.integers(0, 2))
+    Bd = B if per_problem else 1
+    T = 2 * np.pi / max(N, 4)
+    Phi, Gam = P.cw_zoh(T)
+    A = np.broadcast_to(Phi, (Bd, N, 6, 6)).copy()
+    Bm = np.broadcast_to(Gam, (Bd, N, 6, 3)).copy()
+    if rng.integers(0, 2):                                   # break the in-plane / cross-track structure
+        A += 1e-2 * rng.standard_normal(A.shape)
+        Bm += 1e-2 * rng.standard_normal(Bm.shape)
+    c = 1e-2 * rng.standard_normal((Bd, N, 6)) if rng.integers(0, 2) else None
+    has_R = bool(rng.integers(0, 2))
+    R = np.broadcast_to(np.eye(3) * rng.uniform(0.1, 2.0), (Bd, N, 3, 3)).copy() if has_R else None
+    Q = np.broadcast_to(np.diag(rng.uniform(0, 0.1, 6)), (Bd, N + 1, 6, 6)).copy() if rng.integers(0, 2) else None
+    q = 1e-2 * rng.standard_normal((B if rng.integers(0, 2) else 1, n)) if rng.integers(0, 2) else None
+    bt = np.full(nb, P.BLK_NONE, dtype=np.int32)
+    ctrl_types = [P.BLK_L1, P.BLK_L1_BOX, P.BLK_L2, P.BLK_L2_BALL, P.BLK_BOX, P.BLK_BALL, P.BLK_FREE]
+    for k in range(N):
+        bt[3 * k + 2] = ctrl_types[int(rng.integers(0, len(ctrl_types)))]
+        if has_R and rng.random() < 0.2:
+            bt[3 * k + 2] = P.BLK_NONE                      # unsplit control is legal when R > 0
+        if rng.random() < 0.25:                             # some state blocks split too (generic kernel path)
+            bt[3 * k + int(rng.integers(0, 2))] = [P.BLK_BOX, P.BLK_BALL, P.BLK_FREE][int(rng.integers(0, 3))]
+    bt[3 * N] = [P.BLK_POINT, P.BLK_BALL, P.BLK_NONE][int(rng.integers(0, 3))]
+    bt[3 * N + 1] = [P.BLK_POINT, P.BLK_BOX, P.BLK_NONE][int(rng.integers(0, 3))]
+    if not (bt != P.BLK_NONE).any():
+        bt[2] = P.BLK_BOX
+    Bp = B if rng.integers(0, 2) else 1
+    bp = np.zeros((Bp, nb, 8))
+    bp[..., 0] = rng.uniform(0.01, 0.3, (Bp, nb))
+    bp[..., 1] = rng.uniform(0.2, 2.0, (Bp, nb))
+    bp[..., 2:5] = rng.uniform(-0.6, -0.05, (Bp, nb, 3))
+    bp[..., 5:8] = rng.uniform(0.05, 0.6, (Bp, nb, 3))
+    prob = dict(N=N, A=A, B=Bm, c=c, Q=Q, R=R, q=q, s0=0.3 * rng.standard_normal((B, 6)),
+                block_type=bt, block_par=bp)
+    if rng.integers(0, 2):
+        prob["z0"] = 0.1 * rng.standard_normal((B, n))
+        prob["u0"] = 0.1 * rng.standard_normal((B, n))
+    if rng.integers(0, 2):
+        prob["rho0"] = rng.uniform(0.3, 3.0, B)
+    opts = dict(P.DEFAULT_OPTS, rho=float(rng.uniform(0.3, 3.0)), alpha=float(rng.uniform(1.0, 1.8)),
+                max_iter=int(rng.integers(20, 160)), adapt_rho=int(rng.integers(0, 2)),
+                adapt_every=int(rng.integers(2, 9)), adapt_mu=float(rng.uniform(1.5, 10.0)),
+                adapt_until=int(rng.integers(0, 2)) * 60, history=int(rng.integers(0, 2)),
+                chunk=int(rng.integers(0, 2)) * int(rng.integers(1, 40)))
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    assert_bit_identical(got, ref, f"random seed {seed}: N={N} B={B} per_problem={per_problem}")
