@@ -297,7 +297,8 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
-    IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled};
+    static const bool p2_default = getenv("ADMMB_P2") ? atoi(getenv("ADMMB_P2")) != 0 : true;
+    IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default};
     if (FSH && FSMEM) launch_iterate_smem(c, P, adapt);
     else if (FSH) launch_iterate_gshared(c, P, adapt);
     else launch_iterate_pp(c, P, adapt);

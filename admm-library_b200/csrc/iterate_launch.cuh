@@ -7,6 +7,9 @@
 #define ADMMB_ITERATE_ONLY
 #include "kernels.cuh"
 #include "iterate_launch_decl.cuh"
+#ifdef ADMMB_WITH_ITERATE2
+#include "iterate2.cuh"
+#endif
 
 namespace admmb {
 
@@ -80,6 +83,28 @@ static void launch_iterate_tu(const IterLaunchCtx &c, const IterParams &P, bool 
     size_t smem = 16 + ((FSH && FSMEM) ? sizeof(double) * (c.decoupled ? FD : FS) * c.N : 0) +
                   (c.par_batched ? 0 : sizeof(double) * 8 * c.nb) + sizeof(int) * ((c.nb + 3) / 4) * 4;
     smem = round_up(smem, 16);
+#ifdef ADMMB_WITH_ITERATE2
+    // Two problems per thread (iterate2.cuh): +8 % at full width (half the LDS traffic per problem), but a lone
+    // warp gains nothing from the second stream (57 us vs 32 us per iteration for twice the work), so it is used
+    // only when the working set is too wide for the uncapped one-problem build to hold it in one wave.
+    if (FSH && FSMEM && c.two_per_thread && c.fast_pattern && c.decoupled && !c.has_c && !c.has_q && !c.par_batched) {
+        bool lo_fits = false, one_wave = false;
+        if (adapt) pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, true, 2, true>, smem, c.num_sms), P.n_active, &lo_fits);
+        else pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, false, 2, true>, smem, c.num_sms), P.n_active, &lo_fits);
+        if (!lo_fits) {
+            const int half = (P.n_active + 1) / 2;
+            if (adapt) {
+                const int T = pick_block(occ_table(k_admm_iterate2<true>, smem, c.num_sms), half, &one_wave);
+                k_admm_iterate2<true><<<(P.n_active + 2 * T - 1) / (2 * T), T, smem, c.stream>>>(P);
+            } else {
+                const int T = pick_block(occ_table(k_admm_iterate2<false>, smem, c.num_sms), half, &one_wave);
+                k_admm_iterate2<false><<<(P.n_active + 2 * T - 1) / (2 * T), T, smem, c.stream>>>(P);
+            }
+            CK(cudaGetLastError());
+            return;
+        }
+    }
+#endif
 #define DISPATCH(C, Q, A)                                                                              \
     do {                                                                                              \
         if (c.fast_pattern && c.decoupled)                                                            \

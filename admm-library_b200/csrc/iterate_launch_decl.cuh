@@ -7,6 +7,7 @@ struct IterLaunchCtx {
     int num_sms;
     int N, nb;
     bool par_batched, has_c, has_q, fast_pattern, decoupled;
+    bool two_per_thread;          // use the two-problems-per-thread kernel (iterate2.cuh) when eligible
 };
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
