@@ -301,7 +301,7 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
     IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default};
     if (FSH && FSMEM) launch_iterate_smem(c, P, adapt);
     else if (FSH) launch_iterate_gshared(c, P, adapt);
-    else launch_iterate_pp(c, P, adapt);
+    else if (!launch_iterate_pptma(c, P, adapt)) launch_iterate_pp(c, P, adapt);
     ++launches;
 }
 

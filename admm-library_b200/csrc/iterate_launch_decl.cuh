@@ -12,4 +12,6 @@ struct IterLaunchCtx {
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_pp(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+// per-problem factors staged through shared memory by TMA; false when the configuration is not eligible
+bool launch_iterate_pptma(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 }  // namespace admmb

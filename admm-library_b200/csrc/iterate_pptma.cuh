@@ -1,0 +1,204 @@
+// iterate_pptma.cuh -- per-problem models (config 4: every trajectory has its own time-varying STMs): the
+// stage records of the 32 problems of a warp are staged in shared memory by TMA, one stage ahead of the math.
+//
+// Without this the 40-46 factor entries a stage needs are 40-46 dependent-on-nothing-but-latency global loads
+// per thread on the sequential stage chain: measured 212 us per iteration for a lone warp (vs 32 us with a shared
+// factor) and 35 % of the HBM roofline at 16,384 problems.  Here lane 0 of every warp issues two or three
+// cp.async.bulk.tensor.2d boxes ([rows of one stage] x [the warp's 32 columns]) into a two-slot ring and the
+// warp reads its columns back with conflict-free LDS.64 -- "one warp per trajectory group, stage matrices staged
+// in shared memory" (north_star subsystem (1), Riccati-sweep x-update).
+#pragma once
+#include <cuda.h>
+#include "kernels.cuh"
+
+namespace admmb {
+
+constexpr int PPT_ROWS = 52;                       // 46 record rows + 6 (chat / c)
+constexpr int PPT_SLOT_BYTES = PPT_ROWS * 256;     // [row][32 lanes] doubles
+constexpr int PPT_WARPS = 4;
+
+struct PpTmaMaps {
+    CUtensorMap m46, m10, m30, m6;                 // boxes of 46 / 10 / 30 / 6 rows x 32 columns over fac_dec [FD*N][ld]
+};
+
+__device__ __forceinline__ void ppt_tma(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
+}
+
+template <bool HAS_C>
+struct PpStaging {
+    const PpTmaMaps *maps;
+    uint32_t slot[2], bar[2];                      // this warp's ring
+    uint32_t lane8;
+    int col0, N;
+    unsigned *step;                                // uses of the ring so far (warp-uniform, lives in the kernel)
+    bool lane0;
+
+    // step s uses slot s & 1 with mbarrier phase (s >> 1) & 1
+    __device__ __forceinline__ void issue_bwd(int k, unsigned s) const
+    {
+        const uint32_t d = slot[s & 1], b = bar[s & 1];
+        mbar_expect_tx(b, (uint32_t)((46 + (HAS_C ? 6 : 0)) * 256));
+        ppt_tma(d, &maps->m46, col0, k * FD, b);
+        if (HAS_C) ppt_tma(d + 46 * 256, &maps->m6, col0, k * FD + D_CHAT, b);
+    }
+    __device__ __forceinline__ void issue_fwd(int k, unsigned s) const
+    {
+        const uint32_t d = slot[s & 1], b = bar[s & 1];
+        mbar_expect_tx(b, (uint32_t)((40 + (HAS_C ? 6 : 0)) * 256));
+        ppt_tma(d, &maps->m10, col0, k * FD, b);
+        ppt_tma(d + 10 * 256, &maps->m30, col0, k * FD + D_AIN, b);
+        if (HAS_C) ppt_tma(d + 40 * 256, &maps->m6, col0, k * FD + D_C, b);
+    }
+    template <class FR>
+    __device__ __forceinline__ void iter_begin(FR &)
+    {
+        __syncwarp();
+        if (lane0) issue_bwd(N - 1, *step);        // nothing is prefetched across iterations: the factor may have
+    }                                              // been rewritten (adaptive rho) between them
+    template <class FR>
+    __device__ __forceinline__ void bwd_begin(int k, FR &F)
+    {
+        const unsigned s = *step;
+        if (lane0) { if (k > 0) issue_bwd(k - 1, s + 1); else issue_fwd(0, s + 1); }
+        mbar_wait(bar[s & 1], (s >> 1) & 1u);
+        F.sbase = slot[s & 1] + lane8;
+    }
+    template <class FR>
+    __device__ __forceinline__ void fwd_begin(int k, FR &F)
+    {
+        const unsigned s = *step;
+        if (lane0 && k + 1 < N) issue_fwd(k + 1, s + 1);
+        mbar_wait(bar[s & 1], (s >> 1) & 1u);
+        F.sbase = slot[s & 1] + lane8;
+    }
+    __device__ __forceinline__ void stage_end()
+    {
+        __syncwarp();                              // every lane has consumed the slot before it is refilled
+        ++*step;
+    }
+};
+
+// dynamic smem: [16 B mbarrier][par shared ? 8*nb doubles : 0][nb ints, padded][PPT_WARPS x 2 ring mbarriers]
+//               [pad to 128][PPT_WARPS x 2 slots of PPT_SLOT_BYTES]
+template <bool HAS_C, bool HAS_Q, bool ADAPT>
+__global__ void __launch_bounds__(PPT_WARPS * 32, 1)
+k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant__ PpTmaMaps maps)
+{
+    extern __shared__ __align__(128) unsigned char ppt_smem[];
+    unsigned char *smem_raw = ppt_smem;
+    double *parS = reinterpret_cast<double *>(smem_raw + 16);
+    int *bdS = reinterpret_cast<int *>(parS + (P.par_batched ? 0 : 8 * P.nb));
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t par_sbase = (uint32_t)__cvta_generic_to_shared(parS);
+    const uint32_t bd_bytes = (uint32_t)(((P.nb + 3) / 4) * 16);
+    const uint32_t bd_sbase = (uint32_t)__cvta_generic_to_shared(bdS);
+    const uint32_t ring_bars = bd_sbase + bd_bytes;
+    const uint32_t ring = (ring_bars + PPT_WARPS * 2 * 8 + 127u) & ~127u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        for (int i = 0; i < PPT_WARPS * 2; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bars + 8u * i) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        uint32_t bytes = bd_bytes;
+        if (!P.par_batched) bytes += (uint32_t)(8 * P.nb * 8);
+        mbar_expect_tx(mbar, bytes);
+        if (!P.par_batched) bulk_g2s(par_sbase, P.par, (uint32_t)(8 * P.nb * 8), mbar);
+        bulk_g2s(bd_sbase, P.bdesc, bd_bytes, mbar);
+    }
+    __syncthreads();
+    mbar_wait(mbar, 0);
+
+    // every lane of a warp stays in the loop (the ring protocol is warp-collective); lanes without a running
+    // problem compute on a valid column of the same warp tile and never store
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col0 = t - lane;
+    if (col0 >= P.n_active) return;                                 // whole warp beyond the working set
+    const bool owned = t < P.n_active;
+    const size_t p = (size_t)(owned ? t : col0);
+    int st = owned ? P.status[p] : ST_MAX_ITER;
+    const bool was_running = st == ST_RUNNING;
+    if (!__any_sync(0xffffffffu, was_running)) return;
+
+    FacRef<false> F;
+    F.base = P.fac_dec + p;
+    F.ld = P.ld;
+    F.sbase = 0;
+    unsigned step = 0;
+    PpStaging<HAS_C> stg;
+    stg.maps = &maps;
+    stg.slot[0] = ring + (uint32_t)(warp * 2) * PPT_SLOT_BYTES;
+    stg.slot[1] = stg.slot[0] + PPT_SLOT_BYTES;
+    stg.bar[0] = ring_bars + 8u * (warp * 2);
+    stg.bar[1] = stg.bar[0] + 8u;
+    stg.lane8 = 8u * lane;
+    stg.col0 = col0;
+    stg.N = P.N;
+    stg.step = &step;
+    stg.lane0 = lane == 0;
+
+    double rho = P.rho[p];
+    double sigma = ADAPT ? P.usc[p] : 1.0;
+    int it = P.iters[p];
+    double r_norm = 0.0, s_norm = 0.0, eps_pri = 0.0, eps_dual = 0.0;
+    for (int cnt = 0; cnt < P.chunk; ++cnt) {
+        const bool act = st == ST_RUNNING;
+        if (!__any_sync(0xffffffffu, act)) break;
+        double nr[5];
+        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C>>(P, p, F, bdS, par_sbase, rho, sigma, nr, stg, act);
+        if (!act) continue;
+        ++it;
+        sigma = 1.0;
+        r_norm = sqrt(nr[0]);
+        s_norm = rho * sqrt(nr[1]);
+        const double nx = sqrt(nr[2]), nz = sqrt(nr[3]);
+        eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
+        eps_dual = fma(P.reltol, rho * sqrt(nr[4]), P.sqrtn_abs);
+        if (P.hist) {
+            const size_t h = (size_t)(it - 1) * P.hist_ld + (P.orig ? (size_t)P.orig[p] : p);
+            P.hist[h] = r_norm;
+            P.hist[h + P.hist_stride] = s_norm;
+            P.hist[h + 2 * P.hist_stride] = eps_pri;
+            P.hist[h + 3 * P.hist_stride] = eps_dual;
+            P.hist[h + 4 * P.hist_stride] = rho;
+        }
+        if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; continue; }
+        if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; continue; }
+        if (ADAPT && (it % P.every) == 0 && it < P.max_iter && (P.until <= 0 || it <= P.until)) {
+            bool ch = false;
+            if (r_norm > P.mu * s_norm) {
+                if (!(rho * P.tau > RHO_MAX)) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
+            } else if (s_norm > P.mu * r_norm) {
+                if (!(rho * P.inv_tau < RHO_MIN)) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+            }
+            if (ch && P.has_P) {
+                const size_t off = P.raw_batched ? p : 0, ldr = P.raw_batched ? P.ld : 1;
+                int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
+                                             P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
+                                             ldr, rho, bdS, P.fac_rw + p, P.ld);
+                atomicAdd(P.refac_count, 1ULL);
+                if (bad) { st = ST_NAN; continue; }
+                pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
+                __threadfence();                                   // the next iteration's TMA reads must see the new record
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+        }
+        if (it >= P.max_iter) st = ST_MAX_ITER;
+    }
+    if (was_running) {
+        P.iters[p] = it;
+        P.rho[p] = rho;
+        if (ADAPT) P.usc[p] = sigma;
+        P.status[p] = st;
+        P.fin[p] = r_norm;
+        P.fin[p + P.ld] = s_norm;
+        P.fin[p + 2 * P.ld] = eps_pri;
+        P.fin[p + 3 * P.ld] = eps_dual;
+    }
+}
+
+}  // namespace admmb

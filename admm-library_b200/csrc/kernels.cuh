@@ -327,7 +327,8 @@ template <bool SHARED>
 struct FacRef {
     const double *base;
     size_t ld;
-    uint32_t sbase;               // shared-window address of the staged factor (0 when not in smem)
+    uint32_t sbase;               // shared-window address of the staged factor (0 when not in smem); for per-problem
+                                  // factors staged by TMA: address of the current ring slot + 8 * lane
     __device__ __forceinline__ double operator()(int k, int off) const
     {
         if (SHARED) return base[k * FS + off];
@@ -547,7 +548,7 @@ template <class ParFn>
 __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, double alpha, double oma,
                                              const double (&xb)[3], const double (&zo)[3], const double (&uo)[3],
                                              double *zrow, double *urow, size_t ld, double &rr, double &ss,
-                                             double &xx, double &zz, double &uu)
+                                             double &xx, double &zz, double &uu, const bool store = true)
 {
     double v[3], zn[3];
 #pragma unroll
@@ -566,8 +567,10 @@ __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, d
         xx = fma(xb[e], xb[e], xx);
         zz = fma(zn[e], zn[e], zz);
         uu = fma(un, un, uu);
-        ADMMB_ST(zrow + (size_t)e * ld, zn[e]);
-        ADMMB_ST(urow + (size_t)e * ld, un);
+        if (store) {
+            ADMMB_ST(zrow + (size_t)e * ld, zn[e]);
+            ADMMB_ST(urow + (size_t)e * ld, un);
+        }
     }
 }
 
@@ -896,19 +899,44 @@ __device__ __forceinline__ void dec_ld(const FacRef<FSH> &F, int k, int off, dou
         const double2 x = __ldg(q);
         r[0] = x.x; r[1] = x.y;
         if (W == 4) { const double2 y = __ldg(q + 1); r[2] = y.x; r[3] = y.y; }
+    } else if (FSMEM) {
+        // per-problem record staged by TMA: slot rows hold K..Ec (0..45) [+ chat] for the backward sweep and
+        // K (0..9), A, B (10..39) [+ c] for the forward sweep; row = off below 46, off - 36 above; 256 B per row
+        const uint32_t a = F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u;
+#pragma unroll
+        for (int i = 0; i < W; ++i) r[i] = lds64(a + 256u * i);
     } else {
 #pragma unroll
         for (int i = 0; i < W; ++i) r[i] = ADMMB_LD(F.base + ((size_t)k * FD + off + i) * F.ld);
     }
 }
 
+// one entry of the packed record (the affine term c)
+template <bool FSH, bool FSMEM>
+__device__ __forceinline__ double dec_ld1(const FacRef<FSH> &F, int k, int off)
+{
+    if (FSH) return F.base[k * FD + off];
+    if (FSMEM) return lds64(F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u);
+    return F.base[((size_t)k * FD + off) * F.ld];
+}
+
+// hooks of the per-stage factor staging; the default does nothing (factor already addressable)
+struct NoStaging {
+    template <class FR> __device__ __forceinline__ void iter_begin(FR &) {}
+    template <class FR> __device__ __forceinline__ void bwd_begin(int, FR &) {}
+    template <class FR> __device__ __forceinline__ void fwd_begin(int, FR &) {}
+    __device__ __forceinline__ void stage_end() {}
+};
+
 // PD = prefetch distance in stages (even): 2 under the 128-register cap, 4 in the uncapped build, where a
 // lone warp per sub-partition has nothing else to hide the global-load latency behind.
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int PD>
-__device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const size_t p, const FacRef<FSH> F,
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int PD, class Staging = NoStaging>
+__device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const size_t p, FacRef<FSH> F,
                                                    const int *bdesc, const uint32_t par_sbase, const double rho,
-                                                   const double sigma, double (&nr)[5])
+                                                   const double sigma, double (&nr)[5], Staging stg = Staging(),
+                                                   const bool act = true)
 {
+    stg.iter_begin(F);
     const int N = P.N;
     const size_t ld = P.ld;
     const double rinv = 1.0 / rho;
@@ -966,6 +994,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     double *ds = dp + (ptrdiff_t)(N - 1) * ld3;
     auto bwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], const double (&gi_in)[4],
                          const double (&gc_in)[2], double (&pi)[4], double (&pc)[2]) {
+        stg.bwd_begin(k, F);
         double ra[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
@@ -1018,7 +1047,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             acc = fma(er[1], gc[1], acc);
             dj[2] = acc;
         }
-        ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]);
+        if (act) { ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]); }
         ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1049,6 +1078,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             pc[0] = fma(ar[0], gc[l], pc[0]);
             pc[1] = fma(ar[1], gc[l], pc[1]);
         }
+        stg.stage_end();
     };
     // PD == 2 (register-capped build): one guarded copy of the stage body per slot keeps the code small and the
     // register allocator out of spills.  PD == 4 (uncapped build, latency-bound warps): an unguarded main loop
@@ -1091,6 +1121,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     double *zw = zp, *uw = up;
     auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&si)[4],
                          const double (&sc)[2], double (&ni)[4], double (&nc)[2]) {
+        stg.fwd_begin(k, F);
         double a[3], zo[3], uo[3];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1122,7 +1153,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             double pr[8];
             load_par(b, pr);
             block_update(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ld, rr,
-                         ss, xx, zz, uu);
+                         ss, xx, zz, uu, act);
             zw += ld3; uw += ld3;
         }
 #pragma unroll
@@ -1136,7 +1167,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             acc = fma(ar[3], si[3], acc);
             acc = fma(br[0], a[0], acc);
             acc = fma(br[1], a[1], acc);
-            if (HAS_C) acc = acc + F.base[FSH ? (size_t)(k * FD + D_C + (i < 2 ? i : i + 1)) : ((size_t)k * FD + D_C + (i < 2 ? i : i + 1)) * F.ld];
+            if (HAS_C) acc = acc + dec_ld1<FSH, FSMEM>(F, k, D_C + (i < 2 ? i : i + 1));
             ni[i] = acc;
         }
         {
@@ -1149,10 +1180,11 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
                 double acc = ar[0] * sc[0];
                 acc = fma(ar[1], sc[1], acc);
                 acc = fma(bc[i], a[2], acc);
-                if (HAS_C) acc = acc + F.base[FSH ? (size_t)(k * FD + D_C + (i == 0 ? 2 : 5)) : ((size_t)k * FD + D_C + (i == 0 ? 2 : 5)) * F.ld];
+                if (HAS_C) acc = acc + dec_ld1<FSH, FSMEM>(F, k, D_C + (i == 0 ? 2 : 5));
                 nc[i] = acc;
             }
         }
+        stg.stage_end();
     };
     const bool s_in_A = (N & 1) == 0;                   // every stage flips the s ping-pong
     {
@@ -1191,7 +1223,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
         }
         load_par(b, pr);
         block_update(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ld,
-                     up + r0 * ld, ld, rr, ss, xx, zz, uu);
+                     up + r0 * ld, ld, rr, ss, xx, zz, uu, act);
     }
     nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
 }
