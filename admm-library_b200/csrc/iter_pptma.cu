@@ -49,7 +49,7 @@ bool launch_iterate_pptma(const IterLaunchCtx &c, const IterParams &P, bool adap
     maps.m30 = map_rows(P.fac_dec, rows, P.ld, 30);
     maps.m6 = map_rows(P.fac_dec, rows, P.ld, 6);
     size_t smem = 16 + (c.par_batched ? 0 : sizeof(double) * 8 * c.nb) + sizeof(int) * ((c.nb + 3) / 4) * 4 + PPT_WARPS * 2 * 8 +
-                  128 + (size_t)PPT_WARPS * 2 * PPT_SLOT_BYTES;
+                  128 + (size_t)PPT_WARPS * 2 * ppt_slot_bytes(c.has_c);
     smem = round_up(smem, 128);
     const int T = PPT_WARPS * 32;
     const unsigned grid = (unsigned)((P.n_active + T - 1) / T);

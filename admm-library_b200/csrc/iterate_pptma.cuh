@@ -13,8 +13,9 @@
 
 namespace admmb {
 
-constexpr int PPT_ROWS = 52;                       // 46 record rows + 6 (chat / c)
-constexpr int PPT_SLOT_BYTES = PPT_ROWS * 256;     // [row][32 lanes] doubles
+// slot = [rows][32 lanes] doubles: 46 record rows + 6 (chat / c).  Always 52 rows: with the smaller 46-row slots two
+// CTAs fit an SM, the block scheduler co-locates them while other SMs idle, and the kernel gets 8 % slower (measured).
+__host__ __device__ constexpr int ppt_slot_bytes(bool) { return 52 * 256; }
 constexpr int PPT_WARPS = 4;
 
 struct PpTmaMaps {
@@ -82,7 +83,7 @@ struct PpStaging {
 };
 
 // dynamic smem: [16 B mbarrier][par shared ? 8*nb doubles : 0][nb ints, padded][PPT_WARPS x 2 ring mbarriers]
-//               [pad to 128][PPT_WARPS x 2 slots of PPT_SLOT_BYTES]
+//               [pad to 128][PPT_WARPS x 2 slots of ppt_slot_bytes(HAS_C)]
 template <bool HAS_C, bool HAS_Q, bool ADAPT>
 __global__ void __launch_bounds__(PPT_WARPS * 32, 1)
 k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant__ PpTmaMaps maps)
@@ -131,8 +132,8 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
     unsigned step = 0;
     PpStaging<HAS_C> stg;
     stg.maps = &maps;
-    stg.slot[0] = ring + (uint32_t)(warp * 2) * PPT_SLOT_BYTES;
-    stg.slot[1] = stg.slot[0] + PPT_SLOT_BYTES;
+    stg.slot[0] = ring + (uint32_t)(warp * 2) * ppt_slot_bytes(HAS_C);
+    stg.slot[1] = stg.slot[0] + ppt_slot_bytes(HAS_C);
     stg.bar[0] = ring_bars + 8u * (warp * 2);
     stg.bar[1] = stg.bar[0] + 8u;
     stg.lane8 = 8u * lane;

@@ -286,8 +286,9 @@ def main():
     value = total_iters / (dev_ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (k_admm_iterate) ----------------------------------------
-    # algorithmic bytes per problem-iteration: read z,u + write z,u over the split entries (32 n)
-    alg_bytes_per_pi = 32.0 * nsplit
+    # algorithmic bytes per problem-iteration: read z,u + write z,u over the split entries (32 n);
+    # per-problem models additionally stream their packed stage records once per sweep (46 + 40 doubles per stage)
+    alg_bytes_per_pi = 32.0 * nsplit + (86 * 8.0 * N if prob["A"].shape[0] > 1 else 0.0)
     peak, peak_src = measured_peak_hbm()
     achieved = (iters_rank * alg_bytes_per_pi) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic = None
@@ -297,7 +298,7 @@ def main():
             traffic = json.load(open(tpath)).get(name)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_admm_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_admm_iterate_pptma" if prob["A"].shape[0] > 1 else "k_admm_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_problem_iteration": alg_bytes_per_pi,
                 "kernel_ms_per_step": kernel_ms / max(args.steps, 1),
