@@ -231,3 +231,16 @@ def test_random_problem_shapes(solver, cpu_oracle, P, seed):
                 chunk=int(rng.integers(0, 2)) * int(rng.integers(1, 40)))
     got, ref = _both(solver, cpu_oracle, prob, opts)
     assert_bit_identical(got, ref, f"random seed {seed}: N={N} B={B} per_problem={per_problem}")
+
+
+@pytest.mark.parametrize("coupled", [False, True])
+def test_long_horizon_factor_read_from_global(solver, cpu_oracle, P, coupled):
+    """N = 300: the shared factor (88 or 156 doubles x 300 stages) no longer fits the shared-memory budget, so the
+    kernel variants that read it from global memory run (FSH && !FSMEM)."""
+    N = 300
+    prob, opts = P.cfg3_lowthrust_soc(batch=40, N=N, seed=9)
+    if coupled:
+        rng = np.random.default_rng(2)
+        prob = dict(prob, A=prob["A"] + 1e-3 * rng.standard_normal(prob["A"].shape))
+    got, ref = _both(solver, cpu_oracle, prob, dict(opts, max_iter=25, rho=1.0))
+    assert_bit_identical(got, ref, f"N=300 coupled={coupled}")
