@@ -1684,11 +1684,13 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
     for (int b = 0; b < nb; ++b) {
         const int type = bdesc[b] & 0xff;
         if (type == BLK_NONE) {
-            if (rt_out)
+            // unsplit rows of the right-hand side are -q/rho: constant (zero) without a linear cost, written once by
+            // k_dense_rt_init -- rewriting them every iteration was 25 % of this kernel's traffic
+            if (rt_out && q)
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
                     const size_t o = (size_t)(3 * b + e) * ld + p;
-                    put_rt(o, q ? -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv) : 0.0);
+                    put_rt(o, -(q[q_batched ? o : (size_t)(3 * b + e)] * rinv));
                 }
             continue;
         }
