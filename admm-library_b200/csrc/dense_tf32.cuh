@@ -11,6 +11,7 @@
 // roughly FP32 accuracy ("3xTF32") at three times the (cheap) tensor work.
 #pragma once
 #include <cuda.h>
+#include <algorithm>
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -71,37 +72,41 @@ __device__ __forceinline__ void tg_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// grid = (Mpad / 128, ceil(ld / 128)): the M-tiles that share one B (right-hand-side) tile are neighbours in launch
-// order, so they run together and B is fetched from DRAM once, then from L2.  192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2..5 epilogue (TMEM lane quarter = warp % 4).
+// Persistent: grid = min(tiles, SMs); CTA c walks tiles c, c + grid, ... in M-fastest order (the M-tiles that share
+// one right-hand-side tile run side by side, so B is fetched from DRAM once and then from L2).  192 threads: warp 0
+// TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue (TMEM lane quarter = warp % 4).  The
+// accumulator is double-buffered in TMEM (2 x 128 columns): the MMA warp starts tile i+1 while the epilogue warps
+// drain tile i, and the TMA ring never drains between tiles.
 template <int SPLIT>   // 1: plain TF32; 3: hi/lo split operands (Ah*Bh + Ah*Bl + Al*Bh)
 __global__ void __launch_bounds__(192, 1)
 k_dense_xupdate_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                      const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, int n_rows,
-                     int kpad, size_t ldx, float *x, float *dbg = nullptr)
+                     int kpad, size_t ldx, int m_tiles, int n_tiles, float *x, float *dbg = nullptr)
 {
     extern __shared__ __align__(1024) unsigned char tg_dyn_smem[];
-    const uint32_t base = (smem_u32(tg_dyn_smem) + 1023u) & ~1023u;          // 128B swizzle atoms need 1 KB alignment
+    const uint32_t base = (smem_u32(tg_dyn_smem) + 1023u) & ~1023u;      // 128B swizzle atoms need 1 KB alignment
     constexpr int OPERANDS = SPLIT == 3 ? 2 : 1;
     constexpr int TG_STAGES = tg_stages(SPLIT);
     constexpr uint32_t STAGE = TG_STAGE_BYTES * OPERANDS;
-    const uint32_t bars = base + TG_STAGES * STAGE;                      // full[4], empty[4], tmem_full, tmem slot
+    const uint32_t bars = base + TG_STAGES * STAGE;      // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (TG_STAGES + s); };
-    const uint32_t tmem_full = bars + 8u * (2 * TG_STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 1);
+    auto tmem_full = [&](int b) { return bars + 8u * (2 * TG_STAGES + b); };
+    auto tmem_empty = [&](int b) { return bars + 8u * (2 * TG_STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * TG_STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TG_BM, n0 = blockIdx.y * TG_BN;
     const int KB = (kpad + TG_BK - 1) / TG_BK;
+    const int tiles = m_tiles * n_tiles;
+    (void)dbg;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TG_STAGES; ++s) { tg_mbar_init(full(s), 1); tg_mbar_init(empty(s), 1); }
-        tg_mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { tg_mbar_init(tmem_full(b), 1); tg_mbar_init(tmem_empty(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -109,112 +114,105 @@ k_dense_xupdate_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-#ifdef TG_DEBUG_PRESET
-    if (warp >= 2) {   // debug: preset the accumulator to 1.0 to tell "MMA did not write" from "MMA wrote zeros"
-        const uint32_t one = __float_as_uint(1.0f);
-        for (int c = 0; c < 128; ++c)
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + c), "r"(one) : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % TG_STAGES;
-                const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1u;
-                tg_mbar_wait(empty(s), ph ^ 1u);
-                tg_mbar_expect_tx(full(s), STAGE);
-                const uint32_t sa = base + s * STAGE, sb = sa + TG_A_BYTES * OPERANDS;
-                tg_tma_2d(sa, &mapA, kb * TG_BK, m0, full(s));
-                if (SPLIT == 3) tg_tma_2d(sa + TG_A_BYTES, &mapAlo, kb * TG_BK, m0, full(s));
-                for (int c = 0; c < TG_BN / 32; ++c) {
-                    tg_tma_2d(sb + c * TG_B_CHUNK, &mapB, n0 + 32 * c, kb * TG_BK, full(s));
-                    if (SPLIT == 3) tg_tma_2d(sb + TG_B_BYTES + c * TG_B_CHUNK, &mapBlo, n0 + 32 * c, kb * TG_BK, full(s));
+            unsigned g = 0;                                             // ring uses so far
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (t % m_tiles) * TG_BM, n0 = (t / m_tiles) * TG_BN;
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const int s = g % TG_STAGES;
+                    const uint32_t ph = (g / TG_STAGES) & 1u;
+                    tg_mbar_wait(empty(s), ph ^ 1u);
+                    tg_mbar_expect_tx(full(s), STAGE);
+                    const uint32_t sa = base + s * STAGE, sb = sa + TG_A_BYTES * OPERANDS;
+                    tg_tma_2d(sa, &mapA, kb * TG_BK, m0, full(s));
+                    if (SPLIT == 3) tg_tma_2d(sa + TG_A_BYTES, &mapAlo, kb * TG_BK, m0, full(s));
+                    for (int c = 0; c < TG_BN / 32; ++c) {
+                        tg_tma_2d(sb + c * TG_B_CHUNK, &mapB, n0 + 32 * c, kb * TG_BK, full(s));
+                        if (SPLIT == 3) tg_tma_2d(sb + TG_B_BYTES + c * TG_B_CHUNK, &mapBlo, n0 + 32 * c, kb * TG_BK, full(s));
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B tf32, A K-major, B MN-major, N = 128, M = 128
-#ifndef TG_DEBUG_BMAJOR
-#define TG_DEBUG_BMAJOR 1u
-#endif
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (TG_DEBUG_BMAJOR << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(TG_BN >> 3) << 17) |
                                    ((uint32_t)(TG_BM >> 4) << 24);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % TG_STAGES;
-                const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1u;
-                tg_mbar_wait(full(s), ph);
+            unsigned g = 0, li = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++li) {
+                const uint32_t buf = li & 1u;
+                tg_mbar_wait(tmem_empty(buf), ((li >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = base + s * STAGE, sb = sa + TG_A_BYTES * OPERANDS;
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)TG_BN;
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const int s = g % TG_STAGES;
+                    const uint32_t ph = (g / TG_STAGES) & 1u;
+                    tg_mbar_wait(full(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = base + s * STAGE, sb = sa + TG_A_BYTES * OPERANDS;
 #pragma unroll
-                for (int j = 0; j < TG_BK / 8; ++j) {
-                    // A: K-major SW128, one k-step = 32 B inside the 128 B row; 8-row groups 1024 B apart
-                    // B: MN-major SW128/32B: one k-step = two 4-row groups (SBO 512 B) = 1024 B; 32-wide MN atoms
-                    //    (the four TMA boxes of a stage) are TG_B_CHUNK = 4096 B apart (LBO)
-                    const uint64_t ah = tg_desc(sa + 32u * j, 16, 1024, 2);
-                    const uint64_t bh = tg_desc(sb + 1024u * j, TG_B_CHUNK, 512, 1);
-                    #ifdef TG_DEBUG_PRESET
-                    tg_mma_tf32(tmem_base, ah, bh, idesc, 1);
-#else
-                    tg_mma_tf32(tmem_base, ah, bh, idesc, (kb | j) != 0);
-#endif
-                    if (SPLIT == 3) {
-                        const uint64_t al = tg_desc(sa + TG_A_BYTES + 32u * j, 16, 1024, 2);
-                        const uint64_t bl = tg_desc(sb + TG_B_BYTES + 1024u * j, TG_B_CHUNK, 512, 1);
-                        tg_mma_tf32(tmem_base, ah, bl, idesc, 1);
-                        tg_mma_tf32(tmem_base, al, bh, idesc, 1);
+                    for (int j = 0; j < TG_BK / 8; ++j) {
+                        // A: K-major SW128, one k-step = 32 B inside the 128 B row; 8-row groups 1024 B apart
+                        // B: MN-major SW128/32B: one k-step = two 4-row groups (SBO 512 B) = 1024 B; 32-wide MN atoms
+                        //    (the four TMA boxes of a stage) are TG_B_CHUNK = 4096 B apart (LBO)
+                        const uint64_t ah = tg_desc(sa + 32u * j, 16, 1024, 2);
+                        const uint64_t bh = tg_desc(sb + 1024u * j, TG_B_CHUNK, 512, 1);
+                        tg_mma_tf32(d_tmem, ah, bh, idesc, (kb | j) != 0);
+                        if (SPLIT == 3) {
+                            const uint64_t al = tg_desc(sa + TG_A_BYTES + 32u * j, 16, 1024, 2);
+                            const uint64_t bl = tg_desc(sb + TG_B_BYTES + 1024u * j, TG_B_CHUNK, 512, 1);
+                            tg_mma_tf32(d_tmem, ah, bl, idesc, 1);
+                            tg_mma_tf32(d_tmem, al, bh, idesc, 1);
+                        }
                     }
+                    tg_commit(empty(s));                 // ring slot free once these MMAs have read it
                 }
-                tg_commit(empty(s));                 // ring slot free once these MMAs have read it
+                tg_commit(tmem_full(buf));               // accumulator of this tile complete
             }
-            tg_commit(tmem_full);                    // accumulator complete
         }
     } else {
-        tg_mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2) {   // debug: dump the last-used ring slot
-            const int s = (KB - 1) % TG_STAGES;
-            for (int i = lane; i < (int)(STAGE / 4); i += 32) {
-                float v;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + s * STAGE + 4u * i));
-                dbg[i] = v;
-            }
-            if (lane == 0) dbg[16000] = __uint_as_float(tmem_base);
-        }
-        const int q = warp & 3;                      // TMEM lane quarter this warp may read
-        const int row = m0 + 32 * q + lane;
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        unsigned li = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++li) {
+            const int m0 = (t % m_tiles) * TG_BM, n0 = (t / m_tiles) * TG_BN;
+            const uint32_t buf = li & 1u;
+            tg_mbar_wait(tmem_full(buf), (li >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + 32 * q + lane;
 #pragma unroll 1
-        for (int c = 0; c < TG_BN / 32; ++c) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const size_t col = (size_t)n0 + 32 * c;
-            if (row < n_rows && col < ldx) {
-                float4 *dst = reinterpret_cast<float4 *>(x + (size_t)row * ldx + col);
+            for (int c = 0; c < TG_BN / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + buf * (uint32_t)TG_BN + (uint32_t)(32 * c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const size_t col = (size_t)n0 + 32 * c;
+                if (row < n_rows && col < ldx) {
+                    float4 *dst = reinterpret_cast<float4 *>(x + (size_t)row * ldx + col);
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                         __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    for (int v = 0; v < 8; ++v)
+                        dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                }
             }
+            // this warp is done with the accumulator buffer: let the MMA warp reuse it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(buf)) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------
@@ -330,13 +328,16 @@ struct Tf32Plan {
     float *dbg = nullptr;
     void gemm(cudaStream_t st)
     {
-        dim3 grid((unsigned)(mpad / TG_BM), (unsigned)((ld + TG_BN - 1) / TG_BN));
+        const int m_tiles = mpad / TG_BM, n_tiles = (int)((ld + TG_BN - 1) / TG_BN);
+        int dev = 0, sms = NUM_SMS_B200;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned grid = (unsigned)std::min(m_tiles * n_tiles, sms);
         if (split == 3) {
             CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
-            k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, X.p, dbg);
+            k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, m_tiles, n_tiles, X.p, dbg);
         } else {
             CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(1)));
-            k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, X.p, dbg);
+            k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, m_tiles, n_tiles, X.p, dbg);
         }
         CK(cudaGetLastError());
     }

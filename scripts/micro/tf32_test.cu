@@ -47,19 +47,7 @@ int main(int argc, char **argv)
         k_tf32_split_rows<<<g, 128>>>(n, ld, drt.p, plan.Bhi.p, split == 3 ? plan.Blo.p : nullptr);
         cudaMemset(plan.X.p, 0xff, sizeof(float) * plan.mpad * ld);   // NaN pattern: unwritten outputs show up
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        DevBuf<float> dbg; dbg.alloc(16384); cudaMemset(dbg.p, 0, 65536);
-        plan.dbg = dbg.p;
         plan.gemm(0);
-        plan.dbg = nullptr;
-        {
-            std::vector<float> h(16384);
-            cudaMemcpy(h.data(), dbg.p, 65536, cudaMemcpyDeviceToHost);
-            printf("smem A tile row0: "); for (int i = 0; i < 8; ++i) printf("%g ", h[i]); printf("\n");
-            printf("smem A tile row1: "); for (int i = 0; i < 8; ++i) printf("%g ", h[32 + i]); printf("\n");
-            printf("smem B chunk0 krow0: "); for (int i = 0; i < 8; ++i) printf("%g ", h[4096 + i]); printf("\n");
-            printf("smem B chunk0 krow1: "); for (int i = 0; i < 8; ++i) printf("%g ", h[4096 + 32 + i]); printf("\n");
-            { unsigned tb; memcpy(&tb, &h[16000], 4); printf("tmem_base = 0x%08x\n", tb); } int nz = 0; for (int i = 0; i < 8192; ++i) nz += h[i] != 0; printf("nonzeros in stage: %d\n", nz);
-        }
         cudaEventRecord(e0);
         for (int r = 0; r < 10; ++r) plan.gemm(0);
         cudaEventRecord(e1);
