@@ -17,6 +17,9 @@ struct DenseState {
     DevBuf<int> running;              // [1]
     bool ready = false;
     Tf32Plan tf32;                    // tensor-core operands and TMA descriptors (precision = tf32)
+    Tf32Condensed cond;               // the same restricted to the split rows (used when there is no linear cost)
+    DevBuf<int> sblk;                 // split block j -> block number
+    bool condensed = false;
 };
 
 constexpr int DG_BM = 64, DG_BN = 128, DG_BK = 16;

@@ -82,7 +82,22 @@ void dense_run(Shard &s, const admmb_opts *op)
     k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p,
                                               s.has_q ? s.q.p : nullptr, s.q_batched, D.rt.p);
     ++s.launches;
-    if (tf32) {
+    // condensed form: only the split rows take part in the per-iteration GEMM (see dense_tf32.cuh)
+    D.condensed = tf32 && !s.has_q && s.nsplitblk > 0 && getenv("ADMMB_NO_CONDENSED") == nullptr;
+    if (D.condensed) {
+        std::vector<int> R, sb;
+        for (int b = 0; b < nb; ++b)
+            if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
+        D.sblk.alloc(sb.size());
+        CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
+        D.cond.prepare(n, R, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
+        dim3 g((unsigned)((s.batch + 127) / 128), (unsigned)sb.size());
+        k_tf32_rt_init_cond<<<g, 128, 0, s.stream>>>((int)sb.size(), D.sblk.p, s.batch, s.ld, s.z.p, s.u.p, D.cond.Bhi[0].p,
+                                                     split == 3 ? D.cond.Blo[0].p : nullptr);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s.stream));   // R, sb are host temporaries of the async copies above
+        s.launches += 7;
+    } else if (tf32) {
         D.tf32.prepare(n, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
         dim3 g((unsigned)((s.ld + 127) / 128), (unsigned)n);
         k_tf32_split_rows<<<g, 128, 0, s.stream>>>(n, s.ld, D.rt.p, D.tf32.Bhi.p, split == 3 ? D.tf32.Blo.p : nullptr);
@@ -95,35 +110,57 @@ void dense_run(Shard &s, const admmb_opts *op)
     ds.rho = s.rho.p; ds.iters = s.iters.p; ds.status = s.status.p; ds.fin = s.fin.p; ds.running = D.running.p;
     const int chunk = op->chunk > 0 ? op->chunk : 25;
     dim3 gg((unsigned)((s.batch + DG_BN - 1) / DG_BN), (unsigned)((n + DG_BM - 1) / DG_BM));
+    // threads per problem of the condensed prox kernel: enough CTAs x warps to fill the GPU at small batches
+    const int ch = s.batch >= 32768 ? 4 : (s.batch >= 8192 ? 8 : 16);
+    const unsigned gc = (unsigned)((s.batch + 31) / 32);
     int running = 1;
+    bool timing = false;
     for (int it = 1; it <= op->max_iter && running > 0; ++it) {
-        s.kernel_tic();
-        if (tf32) {
-            dense_tf32_xupdate(s);
-        } else {
-            k_dense_xupdate_f64<<<gg, 256, 0, s.stream>>>(n, s.batch, s.ld, D.M.p, D.S.p, D.mc.p, s.s0.p, D.rt.p,
-                                                          s.status.p, D.x.p);
-            ++s.launches;
-        }
+        if (!timing) { s.kernel_tic(); timing = true; }
         const bool check = (it % chunk) == 0 || it == op->max_iter;
         if (check) CK(cudaMemsetAsync(D.running.p, 0, sizeof(int), s.stream));
         ds.it = it;
-        if (tf32)
+        if (D.condensed) {
+            Tf32Condensed &C = D.cond;
+            C.gemm_iter(it, s.stream);
+            const int w = it & 1;
+            float *hi = C.Bhi[w].p, *lo = split == 3 ? C.Blo[w].p : nullptr;
+#define ADMMB_PROX_COND(CH)                                                                                              \
+    k_prox_cond_tf32<CH><<<gc, dim3(32, CH), 0, s.stream>>>(s.nsplitblk, D.sblk.p, s.bdesc.p, s.batch, s.ld, s.par.p,   \
+                                                            s.par_batched, op->alpha, C.Xr.p, s.z.p, s.u.p, hi, lo, ds)
+            if (ch == 4) ADMMB_PROX_COND(4);
+            else if (ch == 8) ADMMB_PROX_COND(8);
+            else ADMMB_PROX_COND(16);
+#undef ADMMB_PROX_COND
+            s.launches += 2;
+        } else if (tf32) {
+            dense_tf32_xupdate(s);
             k_prox_dual_residuals<true, true><<<gb, 128, 0, s.stream>>>(
                 nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched, nullptr, 0.0, op->alpha, D.tf32.X.p, s.z.p, s.u.p,
                 nullptr, D.tf32.Bhi.p, D.tf32.split == 3 ? D.tf32.Blo.p : nullptr, D.x.p, s.has_q ? s.q.p : nullptr,
                 s.q_batched, ds);
-        else
+            s.launches += 2;
+        } else {
+            k_dense_xupdate_f64<<<gg, 256, 0, s.stream>>>(n, s.batch, s.ld, D.M.p, D.S.p, D.mc.p, s.s0.p, D.rt.p,
+                                                          s.status.p, D.x.p);
             k_prox_dual_residuals<true, false><<<gb, 128, 0, s.stream>>>(
                 nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched, nullptr, 0.0, op->alpha, D.x.p, s.z.p, s.u.p,
                 nullptr, D.rt.p, nullptr, nullptr, s.has_q ? s.q.p : nullptr, s.q_batched, ds);
-        ++s.launches;
-        s.kernel_toc();
+            s.launches += 2;
+        }
         CK(cudaGetLastError());
         if (check) {
+            s.kernel_toc();
+            timing = false;
             CK(cudaMemcpyAsync(&running, D.running.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             CK(cudaStreamSynchronize(s.stream));
         }
+    }
+    if (timing) s.kernel_toc();
+    // full x of every problem from the right-hand side of the iteration it finished at
+    if (D.condensed) {
+        D.cond.gemm_final(s.batch, s.iters.p, D.x.p, s.stream);
+        s.launches += 3;
     }
 }
 

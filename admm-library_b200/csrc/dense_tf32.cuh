@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda.h>
 #include <algorithm>
+#include <vector>
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -299,6 +300,29 @@ inline CUtensorMap make_map_2d(const float *ptr, uint64_t rows, uint64_t cols, u
     return m;
 }
 
+// one GEMM launch: X[0..n_rows) = A (mpad x kpad) * B (kpad x ld)
+inline void tf32_launch_gemm(int split, const CUtensorMap &mA, const CUtensorMap &mAlo, const CUtensorMap &mB,
+                             const CUtensorMap &mBlo, int n_rows, int mpad, int kpad, size_t ld, float *X, cudaStream_t st,
+                             float *dbg = nullptr)
+{
+    const int m_tiles = mpad / TG_BM, n_tiles = (int)((ld + TG_BN - 1) / TG_BN);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        sms = NUM_SMS_B200;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const unsigned grid = (unsigned)std::min(m_tiles * n_tiles, sms);
+    if (split == 3) {
+        CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
+        k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
+    } else {
+        CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(1)));
+        k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
+    }
+    CK(cudaGetLastError());
+}
+
 struct Tf32Plan {
     int n = 0, mpad = 0, kpad = 0, split = 1;
     size_t ld = 0;
@@ -326,19 +350,123 @@ struct Tf32Plan {
         mBlo = split == 3 ? make_map_2d(Blo.p, kpad, ld, ld, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : mB;
     }
     float *dbg = nullptr;
-    void gemm(cudaStream_t st)
+    void gemm(cudaStream_t st) { tf32_launch_gemm(split, mA, mAlo, mB, mBlo, n, mpad, kpad, ld, X.p, st, dbg); }
+};
+
+// ---- condensed form ---------------------------------------------------------------------------------
+// When only some rows are split (the control blocks; states are BLK_NONE and there is no linear cost), the
+// right-hand side is zero outside the split rows R and the prox only reads x on R, so the per-iteration GEMM
+// shrinks to X_R = [M[R,R] | S[R] | mc[R]] * [RT_R; s0; 1] (CW, N = 50: 150+7 instead of 456+7 along both M and
+// K: 9x fewer flops, 3x less traffic).  The full x is produced once, after the loop, by one GEMM with
+// A = [M[:,R] | S | mc].  It needs, per problem, the right-hand side of the iteration the problem finished at:
+// the prox kernel therefore writes the next right-hand side into the OTHER of two buffers (iteration `it` reads
+// buffer (it-1)&1 and writes buffer it&1); a finished problem is never written again, so buffer (iters-1)&1 keeps
+// exactly the right-hand side its final x came from.
+
+// A[i][k] = M[rmap(i)][cmap[k]] | S[rmap(i)] | mc[rmap(i)]; rmap == nullptr: identity over n rows
+__global__ void k_tf32_pack_factor_cond(int n, int n_out, int nr, int mpad, int kpad, const int *rmap, const int *cmap,
+                                        const double *M, const double *S, const double *mc, float *hi, float *lo)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (k >= kpad || i >= mpad) return;
+    double v = 0.0;
+    if (i < n_out) {
+        const int ri = rmap ? rmap[i] : i;
+        v = k < nr ? M[(size_t)ri * n + cmap[k]] : (k < nr + 6 ? S[(size_t)ri * 6 + (k - nr)] : (k == nr + 6 ? mc[ri] : 0.0));
+    }
+    const float f = (float)v;
+    const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
+    hi[(size_t)i * kpad + k] = h;
+    if (lo) lo[(size_t)i * kpad + k] = (float)(v - (double)h);
+}
+
+// first right-hand side, compact rows: rt[3j+e] = z - u on split block j (z, u are full-row arrays)
+__global__ void k_tf32_rt_init_cond(int nsb, const int *sblk, int64_t batch, size_t ld, const double *z, const double *u,
+                                    float *hi, float *lo)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (p >= batch || j >= nsb) return;
+    const int b = sblk[j];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
+        const double t = z[o] - u[o];
+        const float f = (float)t;
+        const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
+        hi[oc] = h;
+        if (lo) lo[oc] = (float)(t - (double)h);
+    }
+}
+
+// per problem, copy the right-hand side its final x was computed from (buffer (iters-1)&1) into the final operand
+__global__ void k_tf32_select_final(int rows, int64_t batch, size_t ld, const int *iters, const float *h0, const float *h1,
+                                    const float *l0, const float *l1, float *hi, float *lo)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (p >= batch || r >= rows) return;
+    const int sel = (iters[p] - 1) & 1;
+    const size_t o = (size_t)r * ld + p;
+    hi[o] = sel ? h1[o] : h0[o];
+    if (lo) lo[o] = sel ? l1[o] : l0[o];
+}
+
+struct Tf32Condensed {
+    int n = 0, nr = 0, mpad_r = 0, mpad_n = 0, kpad = 0, split = 1;
+    size_t ld = 0;
+    DevBuf<float> Aihi, Ailo, Afhi, Aflo;        // iteration and final factors
+    DevBuf<float> Bhi[2], Blo[2], Bfhi, Bflo;    // ping-pong right-hand sides, final right-hand side
+    DevBuf<float> Xr, Xf;                        // [mpad_r][ld], [mpad_n][ld]
+    DevBuf<int> rows;                            // R
+    CUtensorMap mAi, mAilo, mAf, mAflo, mB[2], mBlo[2], mBf, mBflo;
+    void prepare(int n_, const std::vector<int> &R, int64_t batch, size_t ld_, int split_, const double *M, const double *S,
+                 const double *mc, const double *s0, cudaStream_t st)
     {
-        const int m_tiles = mpad / TG_BM, n_tiles = (int)((ld + TG_BN - 1) / TG_BN);
-        int dev = 0, sms = NUM_SMS_B200;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned grid = (unsigned)std::min(m_tiles * n_tiles, sms);
-        if (split == 3) {
-            CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
-            k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, m_tiles, n_tiles, X.p, dbg);
-        } else {
-            CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(1)));
-            k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n, kpad, ld, m_tiles, n_tiles, X.p, dbg);
-        }
+        n = n_; nr = (int)R.size(); ld = ld_; split = split_;
+        mpad_r = (int)round_up((size_t)nr, TG_BM);
+        mpad_n = (int)round_up((size_t)n, TG_BM);
+        kpad = (int)round_up((size_t)nr + 7, 8);
+        const bool s3 = split == 3;
+        rows.alloc(nr);
+        CK(cudaMemcpyAsync(rows.p, R.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, st));
+        Aihi.alloc((size_t)mpad_r * kpad); Afhi.alloc((size_t)mpad_n * kpad);
+        if (s3) { Ailo.alloc((size_t)mpad_r * kpad); Aflo.alloc((size_t)mpad_n * kpad); }
+        dim3 g1((unsigned)((kpad + 127) / 128), (unsigned)mpad_r), g2((unsigned)((kpad + 127) / 128), (unsigned)mpad_n);
+        k_tf32_pack_factor_cond<<<g1, 128, 0, st>>>(n, nr, nr, mpad_r, kpad, rows.p, rows.p, M, S, mc, Aihi.p, s3 ? Ailo.p : nullptr);
+        k_tf32_pack_factor_cond<<<g2, 128, 0, st>>>(n, n, nr, mpad_n, kpad, nullptr, rows.p, M, S, mc, Afhi.p, s3 ? Aflo.p : nullptr);
+        CK(cudaGetLastError());
+        auto mk_b = [&](DevBuf<float> &hi, DevBuf<float> &lo) {
+            hi.alloc((size_t)kpad * ld);
+            CK(cudaMemsetAsync(hi.p, 0, sizeof(float) * kpad * ld, st));
+            if (s3) { lo.alloc((size_t)kpad * ld); CK(cudaMemsetAsync(lo.p, 0, sizeof(float) * kpad * ld, st)); }
+            k_tf32_pack_tail<<<(unsigned)((ld + 127) / 128), 128, 0, st>>>(nr, kpad, batch, ld, s0, hi.p, s3 ? lo.p : nullptr);
+            CK(cudaGetLastError());
+        };
+        mk_b(Bhi[0], Blo[0]); mk_b(Bhi[1], Blo[1]); mk_b(Bfhi, Bflo);
+        Xr.alloc((size_t)mpad_r * ld);
+        Xf.alloc((size_t)mpad_n * ld);
+        auto map_a = [&](const float *p, int mp) { return make_map_2d(p, mp, kpad, kpad, TG_BK, TG_BM); };
+        auto map_b = [&](const float *p) { return make_map_2d(p, kpad, ld, ld, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); };
+        mAi = map_a(Aihi.p, mpad_r); mAilo = s3 ? map_a(Ailo.p, mpad_r) : mAi;
+        mAf = map_a(Afhi.p, mpad_n); mAflo = s3 ? map_a(Aflo.p, mpad_n) : mAf;
+        for (int i = 0; i < 2; ++i) { mB[i] = map_b(Bhi[i].p); mBlo[i] = s3 ? map_b(Blo[i].p) : mB[i]; }
+        mBf = map_b(Bfhi.p); mBflo = s3 ? map_b(Bflo.p) : mBf;
+    }
+    // iteration `it` (1-based): reads buffer (it-1)&1
+    void gemm_iter(int it, cudaStream_t st)
+    {
+        const int w = (it - 1) & 1;
+        tf32_launch_gemm(split, mAi, mAilo, mB[w], mBlo[w], nr, mpad_r, kpad, ld, Xr.p, st);
+    }
+    void gemm_final(int64_t batch, const int *iters, double *x_out, cudaStream_t st)
+    {
+        dim3 g((unsigned)((ld + 127) / 128), (unsigned)nr);
+        k_tf32_select_final<<<g, 128, 0, st>>>(nr, batch, ld, iters, Bhi[0].p, Bhi[1].p, Blo[0].p, Blo[1].p, Bfhi.p,
+                                               split == 3 ? Bflo.p : nullptr);
+        tf32_launch_gemm(split, mAf, mAflo, mBf, mBflo, n, mpad_n, kpad, ld, Xf.p, st);
+        dim3 g2((unsigned)((ld + 127) / 128), (unsigned)n);
+        k_tf32_to_double<<<g2, 128, 0, st>>>(n, ld, Xf.p, x_out);
         CK(cudaGetLastError());
     }
 };

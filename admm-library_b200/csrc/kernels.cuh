@@ -1759,6 +1759,93 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
     }
 }
 
+// Condensed TF32 dense path: C3 + C4 + stop test over the split blocks only, several threads per problem.
+// blockDim = (32 problems, CH block-chunks): thread (tx, ty) handles split blocks ty, ty + CH, ... of problem
+// blockIdx.x * 32 + tx, so a warp still touches 32 consecutive problems of one row (coalesced) while the CH
+// warps of a CTA spread the per-problem serial work; the partial norms meet in shared memory and are summed in
+// ascending ty order (deterministic).  x and the right-hand side use compact rows (3j+e for split block j),
+// z, u and par the full rows / block numbers.  The next right-hand side goes to the other ping-pong buffer.
+template <int CH>
+__global__ void __launch_bounds__(32 * CH)
+k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ bdesc, int64_t batch, size_t ld,
+                 const double *par, int par_batched, double alpha, const float *__restrict__ x32, double *z, double *u,
+                 float *rt_hi, float *rt_lo, const DenseStep ds)
+{
+    __shared__ double red[CH][5][32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * 32 + tx;
+    const bool active = p < batch && ds.status[p] == ST_RUNNING;
+    double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
+    double rho = 1.0;
+    if (active) {
+        rho = ds.rho[p];
+        const double rinv = 1.0 / rho;
+        const double oma = 1.0 - alpha;
+        for (int j = ty; j < nsb; j += CH) {
+            const int b = sblk[j];
+            const int type = bdesc[b] & 0xff;
+            double xb[3], zo[3], v[3], zn[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const size_t o = (size_t)(3 * b + e) * ld + p;
+                xb[e] = (double)__ldcs(x32 + (size_t)(3 * j + e) * ld + p);
+                zo[e] = ld_stream(z + o);
+                const double uo = ld_stream(u + o);
+                const double xh = fma(alpha, xb[e], oma * zo[e]);
+                v[e] = xh + uo;
+            }
+            if (par_batched) {
+                const double *pp = par + p + (size_t)(8 * b) * ld;
+                prox_block_dev(type, [&](int q) { return pp[(size_t)q * ld]; }, rinv, v, zn);
+            } else {
+                const double *pp = par + 8 * b;
+                prox_block_dev(type, [&](int q) { return __ldg(pp + q); }, rinv, v, zn);
+            }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
+                const double un = v[e] - zn[e];
+                const double dr = xb[e] - zn[e];
+                const double dz = zn[e] - zo[e];
+                rr = fma(dr, dr, rr);
+                ss = fma(dz, dz, ss);
+                xx = fma(xb[e], xb[e], xx);
+                zz = fma(zn[e], zn[e], zz);
+                uu = fma(un, un, uu);
+                st_stream(z + o, zn[e]);
+                st_stream(u + o, un);
+                const double t = zn[e] - un;
+                const float f = (float)t;
+                const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
+                rt_hi[oc] = h;
+                if (rt_lo) rt_lo[oc] = (float)(t - (double)h);
+            }
+        }
+    }
+    red[ty][0][tx] = rr; red[ty][1][tx] = ss; red[ty][2][tx] = xx; red[ty][3][tx] = zz; red[ty][4][tx] = uu;
+    __syncthreads();
+    if (ty != 0 || !active) return;
+#pragma unroll
+    for (int c = 1; c < CH; ++c) {
+        rr += red[c][0][tx]; ss += red[c][1][tx]; xx += red[c][2][tx]; zz += red[c][3][tx]; uu += red[c][4][tx];
+    }
+    const double r_norm = sqrt(rr), s_norm = rho * sqrt(ss);
+    const double nx = sqrt(xx), nz = sqrt(zz);
+    const double eps_pri = fma(ds.reltol, nx > nz ? nx : nz, ds.sqrtn_abs);
+    const double eps_dual = fma(ds.reltol, rho * sqrt(uu), ds.sqrtn_abs);
+    int st = ST_RUNNING;
+    if (!(isfinite(r_norm) && isfinite(s_norm))) st = ST_NAN;
+    else if (r_norm < eps_pri && s_norm < eps_dual) st = ST_CONVERGED;
+    else if (ds.it >= ds.max_iter) st = ST_MAX_ITER;
+    ds.iters[p] = ds.it;
+    ds.status[p] = st;
+    ds.fin[p] = r_norm;
+    ds.fin[p + ld] = s_norm;
+    ds.fin[p + 2 * ld] = eps_pri;
+    ds.fin[p + 3 * ld] = eps_dual;
+    if (st == ST_RUNNING) atomicAdd(ds.running, 1);
+}
+
 // first right-hand side of the dense path: rt = w*(z - u) - q/rho over full-width rows
 __global__ void k_dense_rt_init(int nb, int64_t batch, size_t ld, const int *bdesc, const double *z,
                                 const double *u, const double *rho, const double *q, int q_batched, double *rt)

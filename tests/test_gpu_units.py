@@ -255,3 +255,46 @@ def test_tf32_dense_path_end_to_end(solver, cpu_oracle, P, case):
     assert np.abs(z[both] - zr[both]).max() <= 1e-3 * sx
     it_ratio = h["iters"][both].astype(float) / hr["iters"][both]
     assert 0.5 < np.median(it_ratio) < 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_iter", [6, 7])
+def test_tf32_condensed_matches_oracle_iterates(solver, cpu_oracle, P, max_iter):
+    """Condensed TF32 path (only the split rows in the per-iteration GEMM, two right-hand-side buffers, full x
+    from one final GEMM): after a FIXED small number of iterations -- far from convergence, so x^k and x^{k+1}
+    differ visibly -- x, z, u must match the FP64 oracle's iterates of the same iteration to TF32x3 accuracy,
+    for an even and an odd count (the final GEMM must pick the right buffer), and must agree with the
+    uncondensed TF32 path."""
+    import os
+    prob, opts = P.cfg2_cw_batch(batch=100, N=20, seed=5)
+    opts = dict(opts, max_iter=max_iter, abstol=1e-12, reltol=1e-12)
+    xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
+    x, z, u, h = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32"))
+    os.environ["ADMMB_NO_CONDENSED"] = "1"
+    try:
+        x2, z2, u2, h2 = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32"))
+    finally:
+        del os.environ["ADMMB_NO_CONDENSED"]
+    assert (h["iters"] == max_iter).all() and (h["status"] == 1).all()
+    sx = np.abs(xr).max()
+    for a, b in ((x, xr), (z, zr), (u, ur), (x, x2), (z, z2), (u, u2)):
+        assert np.abs(a - b).max() <= 2e-5 * sx
+    # x^k and x^{k+1} are far apart at this point: a wrong buffer would fail the check above
+    opts1 = dict(opts, max_iter=max_iter + 1)
+    xn = cpu_oracle.solve(prob, opts1)[0]
+    assert np.abs(xn - xr).max() > 1e-3 * sx
+    np.testing.assert_allclose(h["r_norm"], hr["r_norm"], rtol=1e-3, atol=1e-6 * sx)
+
+
+@pytest.mark.gpu
+def test_tf32_condensed_early_exit_keeps_final_x(solver, cpu_oracle, P):
+    """Problems finish at different iterations; each one's x must come from ITS last iteration: x on the split
+    rows must reproduce the reported primal residual against z."""
+    prob, opts = P.cfg2_cw_batch(batch=256, N=20, seed=9)
+    opts = dict(opts, max_iter=4000, abstol=1e-4, reltol=1e-4, chunk=5)
+    x, z, u, h = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32"))
+    assert (h["status"] == 0).mean() > 0.9 and len(np.unique(h["iters"])) > 5
+    bt = np.asarray(prob["block_type"])
+    rows = np.repeat(bt != P.BLK_NONE, 3)
+    r = np.linalg.norm((x - z)[:, rows], axis=1)
+    np.testing.assert_allclose(r, h["r_norm"], rtol=2e-2, atol=1e-5 * np.abs(x).max())
