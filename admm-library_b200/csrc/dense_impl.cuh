@@ -63,9 +63,117 @@ void dense_prepare(Shard &s, const admmb_opts *)
     D.S.alloc((size_t)s.n * 6);
     D.mc.alloc(s.n);
     D.x.alloc((size_t)s.n * s.ld);
-    D.rt.alloc((size_t)s.n * s.ld);
     D.running.alloc(1);
     D.ready = false;
+}
+
+// The condensed TF32 loop with physical compaction: the still-running problems travel in a dense, 32-aligned
+// working set (the same ColArray machinery as the Riccati path: z, u, rho, iters, status, fin, par and the four
+// right-hand-side buffers incl. their s0 / 1 tail rows); before finished problems are retired their full x is
+// produced by the final GEMM from the right-hand side of their own last iteration.
+void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
+{
+    DenseState &D = s.dense;
+    Tf32Condensed &C = D.cond;
+    const int n = s.n, nb = s.nb;
+    std::vector<int> R, sb;
+    for (int b = 0; b < nb; ++b)
+        if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
+    D.sblk.alloc(sb.size());
+    CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
+    C.prepare(n, R, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
+    {
+        dim3 g((unsigned)((s.batch + 127) / 128), (unsigned)sb.size());
+        k_tf32_rt_init_cond<<<g, 128, 0, s.stream>>>((int)sb.size(), D.sblk.p, s.batch, s.ld, s.z.p, s.u.p, C.Bhi[0].p,
+                                                     split == 3 ? C.Blo[0].p : nullptr);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s.stream));   // R, sb are host temporaries of the async copies above
+    s.launches += 7;
+
+    for (int c = 0; c < Shard::C_COUNT; ++c) s.set_col(c, nullptr, 8, 0, false);
+    s.set_col(Shard::C_Z, s.z.p, 8, n, true);
+    s.set_col(Shard::C_U, s.u.p, 8, n, true);
+    s.set_col(Shard::C_RHO, s.rho.p, 8, 1, false);
+    s.set_col(Shard::C_ITERS, s.iters.p, 4, 1, true);
+    s.set_col(Shard::C_STATUS, s.status.p, 4, 1, true);
+    s.set_col(Shard::C_FIN, s.fin.p, 8, 4, true);
+    s.set_col(Shard::C_PAR, s.par_batched ? s.par.p : nullptr, 8, 8 * nb, false);
+    s.set_col(Shard::C_BH0, C.Bhi[0].p, 4, C.kpad, false);
+    s.set_col(Shard::C_BH1, C.Bhi[1].p, 4, C.kpad, false);
+    s.set_col(Shard::C_BL0, split == 3 ? C.Blo[0].p : nullptr, 4, C.kpad, false);
+    s.set_col(Shard::C_BL1, split == 3 ? C.Blo[1].p : nullptr, 4, C.kpad, false);
+    s.cur_set = -1;
+    s.width = s.batch;
+    s.ld_cur = s.ld;
+    const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
+
+    DenseStep ds;
+    ds.max_iter = op->max_iter;
+    ds.reltol = op->reltol;
+    ds.sqrtn_abs = sqrt((double)s.nsplit) * op->abstol;
+    ds.running = D.running.p;
+    int chunk = op->chunk > 0 ? op->chunk : 25;
+    const int chunk_max = op->chunk > 0 ? op->chunk : 200;
+    int it = 0;
+    while (s.width > 0 && it < op->max_iter) {
+        const int64_t width = s.width;
+        ds.rho = s.colptr<double>(Shard::C_RHO);
+        ds.iters = s.colptr<int>(Shard::C_ITERS);
+        ds.status = s.colptr<int>(Shard::C_STATUS);
+        ds.fin = s.colptr<double>(Shard::C_FIN);
+        double *z = s.colptr<double>(Shard::C_Z), *u = s.colptr<double>(Shard::C_U);
+        const double *par = s.par_batched ? s.colptr<double>(Shard::C_PAR) : s.par.p;
+        // threads per problem of the prox kernel: enough CTAs x warps to fill the GPU at small widths
+        int ch = width >= 32768 ? 4 : (width >= 8192 ? 8 : 16);
+        int pw = ch == 16 ? 16 : (ch == 8 ? 24 : 32);
+        if (const char *e = getenv("ADMMB_PROX_CH")) ch = atoi(e);
+        if (const char *e = getenv("ADMMB_PROX_W")) pw = atoi(e);
+        const unsigned gc = (unsigned)((width + 31) / 32);
+        const int steps = std::min(chunk, op->max_iter - it);
+        s.trace_active.push_back((int)width);
+        s.kernel_tic();
+        for (int k = 0; k < steps; ++k) {
+            ++it;
+            ds.it = it;
+            C.gemm_iter(it, s.stream);
+            float *hi = C.bh[it & 1], *lo = C.bl[it & 1];
+#define ADMMB_PROX_COND(CH, W)                                                                                           \
+    k_prox_cond_tf32<CH, W><<<gc, dim3(32, CH), 0, s.stream>>>(s.nsplitblk, D.sblk.p, s.bdesc.p, width, s.ld_cur, par,  \
+                                                               s.par_batched, op->alpha, C.Xr.p, z, u, hi, lo, ds)
+            if (ch == 4) { if (pw == 16) ADMMB_PROX_COND(4, 16); else if (pw == 24) ADMMB_PROX_COND(4, 24); else ADMMB_PROX_COND(4, 32); }
+            else if (ch == 8) { if (pw == 16) ADMMB_PROX_COND(8, 16); else if (pw == 24) ADMMB_PROX_COND(8, 24); else ADMMB_PROX_COND(8, 32); }
+            else { if (pw == 16) ADMMB_PROX_COND(16, 16); else ADMMB_PROX_COND(16, 32); }
+#undef ADMMB_PROX_COND
+            s.launches += 2;
+        }
+        s.kernel_toc();
+        CK(cudaGetLastError());
+        // who is still running?
+        CK(cudaMemsetAsync(s.split_counts.p, 0, 2 * sizeof(int), s.stream));
+        k_split<<<(unsigned)((width + 255) / 256), 256, 0, s.stream>>>(ds.status, (int)width, s.keep_list.p, s.fin_list.p,
+                                                                      s.split_counts.p);
+        ++s.launches;
+        int cnt[2] = {0, 0};
+        CK(cudaMemcpyAsync(cnt, s.split_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        if (op->chunk <= 0) {   // same launch-length policy as the Riccati path: <= ~2 % of the set finishing per check
+            const int prev = chunk;
+            if (cnt[1] == 0) chunk = std::min(chunk * 2, chunk_max);
+            else chunk = (int)std::min<long long>(chunk_max, std::max<long long>(10, (long long)width * prev / (50LL * cnt[1])));
+        }
+        const bool last = cnt[0] == 0 || it >= op->max_iter;
+        if (cnt[1] == 0) continue;
+        // finished problems idle in the working set until at least 1/32 of it has finished (a repack costs a few
+        // iterations' worth of traffic); a finished problem's buffers are never written again, so retiring it later
+        // is safe
+        if (!last && (no_repack || (int64_t)cnt[1] * 32 < width)) continue;
+        C.final_x(width, ds.iters, s.fin_list.p, cnt[1], s.cur_set < 0 ? nullptr : s.orig[s.cur_set].p, D.x.p, s.ld, s.stream);
+        s.launches += 3;
+        s.repack(last ? 0 : cnt[0], cnt[1]);
+        if (!last) C.bind(s.colptr<float>(Shard::C_BH0), s.colptr<float>(Shard::C_BH1), s.colptr<float>(Shard::C_BL0),
+                          s.colptr<float>(Shard::C_BL1), s.ld_cur);
+    }
 }
 
 void dense_run(Shard &s, const admmb_opts *op)
@@ -79,25 +187,17 @@ void dense_run(Shard &s, const admmb_opts *op)
     const bool tf32 = op->precision == ADMMB_PREC_TF32;
     const int split = getenv("ADMMB_TF32_SINGLE") ? 1 : 3;
     CK(cudaMemsetAsync(D.x.p, 0, sizeof(double) * (size_t)n * s.ld, s.stream));
-    k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p,
-                                              s.has_q ? s.q.p : nullptr, s.q_batched, D.rt.p);
-    ++s.launches;
     // condensed form: only the split rows take part in the per-iteration GEMM (see dense_tf32.cuh)
     D.condensed = tf32 && !s.has_q && s.nsplitblk > 0 && getenv("ADMMB_NO_CONDENSED") == nullptr;
     if (D.condensed) {
-        std::vector<int> R, sb;
-        for (int b = 0; b < nb; ++b)
-            if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
-        D.sblk.alloc(sb.size());
-        CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
-        D.cond.prepare(n, R, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
-        dim3 g((unsigned)((s.batch + 127) / 128), (unsigned)sb.size());
-        k_tf32_rt_init_cond<<<g, 128, 0, s.stream>>>((int)sb.size(), D.sblk.p, s.batch, s.ld, s.z.p, s.u.p, D.cond.Bhi[0].p,
-                                                     split == 3 ? D.cond.Blo[0].p : nullptr);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(s.stream));   // R, sb are host temporaries of the async copies above
-        s.launches += 7;
-    } else if (tf32) {
+        dense_run_condensed(s, op, split);
+        return;
+    }
+    D.rt.alloc((size_t)s.n * s.ld);
+    k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p,
+                                              s.has_q ? s.q.p : nullptr, s.q_batched, D.rt.p);
+    ++s.launches;
+    if (tf32) {
         D.tf32.prepare(n, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
         dim3 g((unsigned)((s.ld + 127) / 128), (unsigned)n);
         k_tf32_split_rows<<<g, 128, 0, s.stream>>>(n, s.ld, D.rt.p, D.tf32.Bhi.p, split == 3 ? D.tf32.Blo.p : nullptr);
@@ -110,9 +210,6 @@ void dense_run(Shard &s, const admmb_opts *op)
     ds.rho = s.rho.p; ds.iters = s.iters.p; ds.status = s.status.p; ds.fin = s.fin.p; ds.running = D.running.p;
     const int chunk = op->chunk > 0 ? op->chunk : 25;
     dim3 gg((unsigned)((s.batch + DG_BN - 1) / DG_BN), (unsigned)((n + DG_BM - 1) / DG_BM));
-    // threads per problem of the condensed prox kernel: enough CTAs x warps to fill the GPU at small batches
-    const int ch = s.batch >= 32768 ? 4 : (s.batch >= 8192 ? 8 : 16);
-    const unsigned gc = (unsigned)((s.batch + 31) / 32);
     int running = 1;
     bool timing = false;
     for (int it = 1; it <= op->max_iter && running > 0; ++it) {
@@ -120,20 +217,7 @@ void dense_run(Shard &s, const admmb_opts *op)
         const bool check = (it % chunk) == 0 || it == op->max_iter;
         if (check) CK(cudaMemsetAsync(D.running.p, 0, sizeof(int), s.stream));
         ds.it = it;
-        if (D.condensed) {
-            Tf32Condensed &C = D.cond;
-            C.gemm_iter(it, s.stream);
-            const int w = it & 1;
-            float *hi = C.Bhi[w].p, *lo = split == 3 ? C.Blo[w].p : nullptr;
-#define ADMMB_PROX_COND(CH)                                                                                              \
-    k_prox_cond_tf32<CH><<<gc, dim3(32, CH), 0, s.stream>>>(s.nsplitblk, D.sblk.p, s.bdesc.p, s.batch, s.ld, s.par.p,   \
-                                                            s.par_batched, op->alpha, C.Xr.p, s.z.p, s.u.p, hi, lo, ds)
-            if (ch == 4) ADMMB_PROX_COND(4);
-            else if (ch == 8) ADMMB_PROX_COND(8);
-            else ADMMB_PROX_COND(16);
-#undef ADMMB_PROX_COND
-            s.launches += 2;
-        } else if (tf32) {
+        if (tf32) {
             dense_tf32_xupdate(s);
             k_prox_dual_residuals<true, true><<<gb, 128, 0, s.stream>>>(
                 nb, s.batch, s.ld, s.bdesc.p, s.par.p, s.par_batched, nullptr, 0.0, op->alpha, D.tf32.X.p, s.z.p, s.u.p,
@@ -157,11 +241,6 @@ void dense_run(Shard &s, const admmb_opts *op)
         }
     }
     if (timing) s.kernel_toc();
-    // full x of every problem from the right-hand side of the iteration it finished at
-    if (D.condensed) {
-        D.cond.gemm_final(s.batch, s.iters.p, D.x.p, s.stream);
-        s.launches += 3;
-    }
 }
 
 void dense_output(Shard &s, double *xo, double *zo, double *uo)

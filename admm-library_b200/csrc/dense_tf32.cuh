@@ -412,13 +412,24 @@ __global__ void k_tf32_select_final(int rows, int64_t batch, size_t ld, const in
     if (lo) lo[o] = sel ? l1[o] : l0[o];
 }
 
+// x_home[r][orig[c]] = (double) xf[r][c] for the finished working-set columns c = fin[t]
+__global__ void k_tf32_scatter_x(int rows, const float *xf, size_t ld_in, const int *fin, int n_fin, const int *orig,
+                                 double *home, size_t ld_home)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_fin) return;
+    const size_t c = (size_t)fin[t], h = orig ? (size_t)orig[c] : c;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) home[(size_t)r * ld_home + h] = (double)xf[(size_t)r * ld_in + c];
+}
+
 struct Tf32Condensed {
     int n = 0, nr = 0, mpad_r = 0, mpad_n = 0, kpad = 0, split = 1;
-    size_t ld = 0;
+    size_t ld = 0, ld_cur = 0;
     DevBuf<float> Aihi, Ailo, Afhi, Aflo;        // iteration and final factors
-    DevBuf<float> Bhi[2], Blo[2], Bfhi, Bflo;    // ping-pong right-hand sides, final right-hand side
+    DevBuf<float> Bhi[2], Blo[2], Bfhi, Bflo;    // ping-pong right-hand sides (home copies), final right-hand side
     DevBuf<float> Xr, Xf;                        // [mpad_r][ld], [mpad_n][ld]
     DevBuf<int> rows;                            // R
+    float *bh[2] = {nullptr, nullptr}, *bl[2] = {nullptr, nullptr};   // the buffers of the current working set
     CUtensorMap mAi, mAilo, mAf, mAflo, mB[2], mBlo[2], mBf, mBflo;
     void prepare(int n_, const std::vector<int> &R, int64_t batch, size_t ld_, int split_, const double *M, const double *S,
                  const double *mc, const double *s0, cudaStream_t st)
@@ -443,30 +454,44 @@ struct Tf32Condensed {
             k_tf32_pack_tail<<<(unsigned)((ld + 127) / 128), 128, 0, st>>>(nr, kpad, batch, ld, s0, hi.p, s3 ? lo.p : nullptr);
             CK(cudaGetLastError());
         };
-        mk_b(Bhi[0], Blo[0]); mk_b(Bhi[1], Blo[1]); mk_b(Bfhi, Bflo);
+        mk_b(Bhi[0], Blo[0]); mk_b(Bhi[1], Blo[1]);
+        Bfhi.alloc((size_t)kpad * ld);
+        if (s3) Bflo.alloc((size_t)kpad * ld);
         Xr.alloc((size_t)mpad_r * ld);
         Xf.alloc((size_t)mpad_n * ld);
-        auto map_a = [&](const float *p, int mp) { return make_map_2d(p, mp, kpad, kpad, TG_BK, TG_BM); };
-        auto map_b = [&](const float *p) { return make_map_2d(p, kpad, ld, ld, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); };
-        mAi = map_a(Aihi.p, mpad_r); mAilo = s3 ? map_a(Ailo.p, mpad_r) : mAi;
-        mAf = map_a(Afhi.p, mpad_n); mAflo = s3 ? map_a(Aflo.p, mpad_n) : mAf;
-        for (int i = 0; i < 2; ++i) { mB[i] = map_b(Bhi[i].p); mBlo[i] = s3 ? map_b(Blo[i].p) : mB[i]; }
+        mAi = make_map_2d(Aihi.p, mpad_r, kpad, kpad, TG_BK, TG_BM);
+        mAilo = s3 ? make_map_2d(Ailo.p, mpad_r, kpad, kpad, TG_BK, TG_BM) : mAi;
+        mAf = make_map_2d(Afhi.p, mpad_n, kpad, kpad, TG_BK, TG_BM);
+        mAflo = s3 ? make_map_2d(Aflo.p, mpad_n, kpad, kpad, TG_BK, TG_BM) : mAf;
+        bind(Bhi[0].p, Bhi[1].p, Blo[0].p, Blo[1].p, ld);
+    }
+    // point the GEMMs at the right-hand-side buffers of the current working set (pitch ld_now)
+    void bind(float *h0, float *h1, float *l0, float *l1, size_t ld_now)
+    {
+        const bool s3 = split == 3;
+        ld_cur = ld_now;
+        bh[0] = h0; bh[1] = h1; bl[0] = s3 ? l0 : nullptr; bl[1] = s3 ? l1 : nullptr;
+        auto map_b = [&](const float *p) { return make_map_2d(p, kpad, ld_cur, ld_cur, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); };
+        for (int i = 0; i < 2; ++i) { mB[i] = map_b(bh[i]); mBlo[i] = s3 ? map_b(bl[i]) : mB[i]; }
         mBf = map_b(Bfhi.p); mBflo = s3 ? map_b(Bflo.p) : mBf;
     }
-    // iteration `it` (1-based): reads buffer (it-1)&1
+    // iteration `it` (1-based): reads buffer (it-1)&1; the prox kernel then writes buffer it&1
     void gemm_iter(int it, cudaStream_t st)
     {
         const int w = (it - 1) & 1;
-        tf32_launch_gemm(split, mAi, mAilo, mB[w], mBlo[w], nr, mpad_r, kpad, ld, Xr.p, st);
+        tf32_launch_gemm(split, mAi, mAilo, mB[w], mBlo[w], nr, mpad_r, kpad, ld_cur, Xr.p, st);
     }
-    void gemm_final(int64_t batch, const int *iters, double *x_out, cudaStream_t st)
+    // full x of the finished columns fin[0..n_fin) of the working set (width columns), written to their home columns
+    void final_x(int64_t width, const int *iters, const int *fin, int n_fin, const int *orig, double *x_home, size_t ld_home,
+                 cudaStream_t st)
     {
-        dim3 g((unsigned)((ld + 127) / 128), (unsigned)nr);
-        k_tf32_select_final<<<g, 128, 0, st>>>(nr, batch, ld, iters, Bhi[0].p, Bhi[1].p, Blo[0].p, Blo[1].p, Bfhi.p,
-                                               split == 3 ? Bflo.p : nullptr);
-        tf32_launch_gemm(split, mAf, mAflo, mBf, mBflo, n, mpad_n, kpad, ld, Xf.p, st);
-        dim3 g2((unsigned)((ld + 127) / 128), (unsigned)n);
-        k_tf32_to_double<<<g2, 128, 0, st>>>(n, ld, Xf.p, x_out);
+        if (n_fin <= 0) return;
+        const bool s3 = split == 3;
+        dim3 g((unsigned)((width + 127) / 128), (unsigned)kpad);   // the tail rows (s0, 1) travel with the buffers
+        k_tf32_select_final<<<g, 128, 0, st>>>(kpad, width, ld_cur, iters, bh[0], bh[1], bl[0], bl[1], Bfhi.p, s3 ? Bflo.p : nullptr);
+        tf32_launch_gemm(split, mAf, mAflo, mBf, mBflo, n, mpad_n, kpad, ld_cur, Xf.p, st);
+        dim3 g2((unsigned)((n_fin + 127) / 128), (unsigned)std::min(n, 64));
+        k_tf32_scatter_x<<<g2, 128, 0, st>>>(n, Xf.p, ld_cur, fin, n_fin, orig, x_home, ld_home);
         CK(cudaGetLastError());
     }
 };

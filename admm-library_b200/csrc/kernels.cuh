@@ -1765,8 +1765,8 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
 // warps of a CTA spread the per-problem serial work; the partial norms meet in shared memory and are summed in
 // ascending ty order (deterministic).  x and the right-hand side use compact rows (3j+e for split block j),
 // z, u and par the full rows / block numbers.  The next right-hand side goes to the other ping-pong buffer.
-template <int CH>
-__global__ void __launch_bounds__(32 * CH)
+template <int CH, int MINW>   // MINW: resident warps per SM the register allocation must allow
+__global__ void __launch_bounds__(32 * CH, MINW / CH)
 k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ bdesc, int64_t batch, size_t ld,
                  const double *par, int par_batched, double alpha, const float *__restrict__ x32, double *z, double *u,
                  float *rt_hi, float *rt_lo, const DenseStep ds)
@@ -1843,8 +1843,7 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
     ds.fin[p + ld] = s_norm;
     ds.fin[p + 2 * ld] = eps_pri;
     ds.fin[p + 3 * ld] = eps_dual;
-    if (st == ST_RUNNING) atomicAdd(ds.running, 1);
-}
+    }
 
 // first right-hand side of the dense path: rt = w*(z - u) - q/rho over full-width rows
 __global__ void k_dense_rt_init(int nb, int64_t batch, size_t ld, const int *bdesc, const double *z,

@@ -195,6 +195,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--xupdate", default="riccati", choices=["riccati", "dense"],
+                    help="x-update of the solve (default: the bit-exact FP64 Riccati path)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "tf32"],
+                    help="tf32 (with --xupdate dense): the tcgen05 TF32x3 GEMM path, a stated 1e-4 precision class")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,6 +225,8 @@ def main():
     prob, opts = make_workload(pkg.problems, name, per_gpu, rank)
     if args.chunk:
         opts["chunk"] = args.chunk
+    if args.xupdate != "riccati" or args.precision != "f64":
+        opts["xupdate"], opts["precision"] = args.xupdate, args.precision
     N = int(prob["A"].shape[1])
     n = 9 * N + 6
     nsplit = nsplit_of(prob)
@@ -370,9 +376,11 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / max(args.steps, 1),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64" if args.precision == "f64" else "tf32x3 x-update (fp32 accumulate), f64 prox/dual/residuals",
                 "data": "synthetic",
-                "config": {"workload": WORKLOADS[name][3], "name": name, "problems_per_gpu": per_gpu,
+                "config": {"workload": WORKLOADS[name][3], "name": name, "xupdate": args.xupdate,
+                           "problems_per_gpu": per_gpu,
                            "problems_total": per_gpu * world, "N": N, "n": n, "split_entries": nsplit,
                            "tolerance": 1e-6, "max_iter": opts["max_iter"], "rho": opts["rho"],
                            "alpha": opts["alpha"], "adapt_rho": opts["adapt_rho"],
