@@ -96,7 +96,7 @@ struct Shard {
     // the working set: per-problem arrays that travel with the still-running problems (physical
     // compaction); set -1 = the home arrays themselves, 0/1 = dense ping-pong copies
     enum { C_Z, C_U, C_D, C_S0, C_RHO, C_USC, C_ITERS, C_STATUS, C_FIN, C_Q, C_PAR, C_FAC, C_FACDEC, C_RAWA, C_RAWB,
-           C_RAWC, C_RAWQ, C_RAWR, C_BH0, C_BH1, C_BL0, C_BL1, C_COUNT };
+           C_RAWC, C_RAWQ, C_RAWR, C_XACC, C_BH, C_BL, C_COUNT };
     struct ColArray {
         void *home = nullptr;
         size_t elem = 8;

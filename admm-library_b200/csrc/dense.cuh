@@ -13,8 +13,8 @@ namespace admmb {
 
 struct DenseState {
     DevBuf<double> M, S, mc;          // [n][n] row-major, [n][6], [n]
-    DevBuf<double> x, rt, norms;      // [n][ld], [n][ld], [5][ld]
-    DevBuf<int> running;              // [1]
+    DevBuf<double> x, rt, norms, dscr; // [n][ld], [n][ld], [5][ld], [3N][ld] (Riccati scratch of the condensed path)
+    DevBuf<int> running, itbase;      // [1], [1] (iteration counter of the graph replays)
     bool ready = false;
     Tf32Plan tf32;                    // tensor-core operands and TMA descriptors (precision = tf32)
     Tf32Condensed cond;               // the same restricted to the split rows (used when there is no linear cost)

@@ -67,54 +67,64 @@ void dense_prepare(Shard &s, const admmb_opts *)
     D.ready = false;
 }
 
-// The condensed TF32 loop with physical compaction: the still-running problems travel in a dense, 32-aligned
-// working set (the same ColArray machinery as the Riccati path: z, u, rho, iters, status, fin, par and the four
-// right-hand-side buffers incl. their s0 / 1 tail rows); before finished problems are retired their full x is
-// produced by the final GEMM from the right-hand side of their own last iteration.
+// The condensed incremental TF32 loop (see dense_tf32.cuh) with physical compaction: the still-running problems
+// travel in a dense, 32-aligned working set (the same ColArray machinery as the Riccati path: z, u, x_R, s0, rho,
+// iters, status, fin, par and the increment buffers); a finished problem's full x is computed when it retires.
 void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
 {
     DenseState &D = s.dense;
     Tf32Condensed &C = D.cond;
-    const int n = s.n, nb = s.nb;
+    const int n = s.n, nb = s.nb, N = s.N;
+    const unsigned gb = (unsigned)((s.batch + 127) / 128);
     std::vector<int> R, sb;
     for (int b = 0; b < nb; ++b)
         if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
     D.sblk.alloc(sb.size());
     CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
-    C.prepare(n, R, s.batch, s.ld, split, D.M.p, D.S.p, D.mc.p, s.s0.p, s.stream);
+    C.prepare(n, R, s.ld, split, D.M.p, s.stream);
+    // x^1 exactly: one FP64 Riccati x-update of the initial right-hand side, then x_R = its split rows
+    D.rt.alloc((size_t)n * s.ld);
+    D.dscr.alloc((size_t)3 * N * s.ld);
+    k_dense_rt_init<<<gb, 128, 0, s.stream>>>(nb, s.batch, s.ld, s.bdesc.p, s.z.p, s.u.p, s.rho.p, nullptr, 0, D.rt.p);
+    if (s.has_c) k_xupdate_riccati<true><<<gb, 128, 0, s.stream>>>(N, s.batch, s.ld, s.fac.p, s.s0.p, D.rt.p, D.dscr.p, D.x.p);
+    else k_xupdate_riccati<false><<<gb, 128, 0, s.stream>>>(N, s.batch, s.ld, s.fac.p, s.s0.p, D.rt.p, D.dscr.p, D.x.p);
     {
-        dim3 g((unsigned)((s.batch + 127) / 128), (unsigned)sb.size());
-        k_tf32_rt_init_cond<<<g, 128, 0, s.stream>>>((int)sb.size(), D.sblk.p, s.batch, s.ld, s.z.p, s.u.p, C.Bhi[0].p,
-                                                     split == 3 ? C.Blo[0].p : nullptr);
-        CK(cudaGetLastError());
+        dim3 g(gb, (unsigned)C.nr);
+        k_tf32_gather_rows<<<g, 128, 0, s.stream>>>(C.nr, C.rows.p, s.batch, s.ld, D.x.p, C.Xacc.p);
     }
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s.stream));   // R, sb are host temporaries of the async copies above
-    s.launches += 7;
+    s.launches += 4;
 
     for (int c = 0; c < Shard::C_COUNT; ++c) s.set_col(c, nullptr, 8, 0, false);
     s.set_col(Shard::C_Z, s.z.p, 8, n, true);
     s.set_col(Shard::C_U, s.u.p, 8, n, true);
+    s.set_col(Shard::C_XACC, C.Xacc.p, 8, C.nr, false);
+    s.set_col(Shard::C_S0, s.s0.p, 8, 6, false);
     s.set_col(Shard::C_RHO, s.rho.p, 8, 1, false);
     s.set_col(Shard::C_ITERS, s.iters.p, 4, 1, true);
     s.set_col(Shard::C_STATUS, s.status.p, 4, 1, true);
     s.set_col(Shard::C_FIN, s.fin.p, 8, 4, true);
     s.set_col(Shard::C_PAR, s.par_batched ? s.par.p : nullptr, 8, 8 * nb, false);
-    s.set_col(Shard::C_BH0, C.Bhi[0].p, 4, C.kpad, false);
-    s.set_col(Shard::C_BH1, C.Bhi[1].p, 4, C.kpad, false);
-    s.set_col(Shard::C_BL0, split == 3 ? C.Blo[0].p : nullptr, 4, C.kpad, false);
-    s.set_col(Shard::C_BL1, split == 3 ? C.Blo[1].p : nullptr, 4, C.kpad, false);
+    s.set_col(Shard::C_BH, C.Bhi.p, 4, C.kpad, false);
+    s.set_col(Shard::C_BL, split == 3 ? C.Blo.p : nullptr, 4, C.kpad, false);
     s.cur_set = -1;
     s.width = s.batch;
     s.ld_cur = s.ld;
     const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
 
-    DenseStep ds;
+    DenseStep ds{};
     ds.max_iter = op->max_iter;
     ds.reltol = op->reltol;
     ds.sqrtn_abs = sqrt((double)s.nsplit) * op->abstol;
     ds.running = D.running.p;
     int chunk = op->chunk > 0 ? op->chunk : 25;
     const int chunk_max = op->chunk > 0 ? op->chunk : 200;
+    constexpr int GRAPH_ITERS = 20;
+    const bool use_graphs = getenv("ADMMB_NO_GRAPH") == nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    struct GraphGuard { cudaGraphExec_t &g; ~GraphGuard() { if (g) cudaGraphExecDestroy(g); } } guard{gexec};
+    D.itbase.alloc(1);
     int it = 0;
     while (s.width > 0 && it < op->max_iter) {
         const int64_t width = s.width;
@@ -123,6 +133,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         ds.status = s.colptr<int>(Shard::C_STATUS);
         ds.fin = s.colptr<double>(Shard::C_FIN);
         double *z = s.colptr<double>(Shard::C_Z), *u = s.colptr<double>(Shard::C_U);
+        double *xacc = s.colptr<double>(Shard::C_XACC);
         const double *par = s.par_batched ? s.colptr<double>(Shard::C_PAR) : s.par.p;
         // threads per problem of the prox kernel: enough CTAs x warps to fill the GPU at small widths
         int ch = width >= 32768 ? 4 : (width >= 8192 ? 8 : 16);
@@ -132,20 +143,45 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         const unsigned gc = (unsigned)((width + 31) / 32);
         const int steps = std::min(chunk, op->max_iter - it);
         s.trace_active.push_back((int)width);
-        s.kernel_tic();
-        for (int k = 0; k < steps; ++k) {
-            ++it;
-            ds.it = it;
-            C.gemm_iter(it, s.stream);
-            float *hi = C.bh[it & 1], *lo = C.bl[it & 1];
+        auto launch_iter = [&](const DenseStep &d) {
+            C.gemm(s.stream);
 #define ADMMB_PROX_COND(CH, W)                                                                                           \
     k_prox_cond_tf32<CH, W><<<gc, dim3(32, CH), 0, s.stream>>>(s.nsplitblk, D.sblk.p, s.bdesc.p, width, s.ld_cur, par,  \
-                                                               s.par_batched, op->alpha, C.Xr.p, z, u, hi, lo, ds)
+                                                               s.par_batched, op->alpha, C.Xr.p, xacc, z, u, C.bh, C.bl, d)
             if (ch == 4) { if (pw == 16) ADMMB_PROX_COND(4, 16); else if (pw == 24) ADMMB_PROX_COND(4, 24); else ADMMB_PROX_COND(4, 32); }
             else if (ch == 8) { if (pw == 16) ADMMB_PROX_COND(8, 16); else if (pw == 24) ADMMB_PROX_COND(8, 24); else ADMMB_PROX_COND(8, 32); }
             else { if (pw == 16) ADMMB_PROX_COND(16, 16); else ADMMB_PROX_COND(16, 32); }
 #undef ADMMB_PROX_COND
             s.launches += 2;
+        };
+        s.kernel_tic();
+        int k = 0;
+        // long chunks replay a captured graph of GRAPH_ITERS iterations (2 launches each): the loop is launch-bound
+        // at small widths; the iteration number then comes from a device counter.  The graph bakes in the pointers
+        // of the current working set, so it is dropped at every repack.
+        if (use_graphs && steps >= 2 * GRAPH_ITERS) {
+            if (!gexec) {
+                cudaGraph_t g = nullptr;
+                DenseStep dg = ds;
+                dg.it_base = D.itbase.p;
+                CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+                for (int q = 1; q <= GRAPH_ITERS; ++q) { dg.it = q; launch_iter(dg); }
+                k_add_int<<<1, 1, 0, s.stream>>>(D.itbase.p, GRAPH_ITERS);
+                CK(cudaStreamEndCapture(s.stream, &g));
+                CK(cudaGraphInstantiate(&gexec, g, 0));
+                cudaGraphDestroy(g);
+                s.launches -= 2 * GRAPH_ITERS;   // captured, not launched
+            }
+            k_set_int<<<1, 1, 0, s.stream>>>(D.itbase.p, it);
+            for (; steps - k >= GRAPH_ITERS; k += GRAPH_ITERS, it += GRAPH_ITERS) {
+                CK(cudaGraphLaunch(gexec, s.stream));
+                s.launches += 2 * GRAPH_ITERS + 1;
+            }
+        }
+        for (; k < steps; ++k) {
+            ++it;
+            ds.it = it;
+            launch_iter(ds);
         }
         s.kernel_toc();
         CK(cudaGetLastError());
@@ -165,14 +201,20 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         const bool last = cnt[0] == 0 || it >= op->max_iter;
         if (cnt[1] == 0) continue;
         // finished problems idle in the working set until at least 1/32 of it has finished (a repack costs a few
-        // iterations' worth of traffic); a finished problem's buffers are never written again, so retiring it later
+        // iterations' worth of traffic); a finished problem's columns are never written again, so retiring it later
         // is safe
         if (!last && (no_repack || (int64_t)cnt[1] * 32 < width)) continue;
-        C.final_x(width, ds.iters, s.fin_list.p, cnt[1], s.cur_set < 0 ? nullptr : s.orig[s.cur_set].p, D.x.p, s.ld, s.stream);
-        s.launches += 3;
+        {
+            const unsigned gf = (unsigned)((cnt[1] + 63) / 64);
+            const int *orig = s.cur_set < 0 ? nullptr : s.orig[s.cur_set].p;
+            const double *s0w = s.colptr<double>(Shard::C_S0);
+            if (s.has_c) k_tf32_final_x<true><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld);
+            else k_tf32_final_x<false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld);
+            ++s.launches;
+        }
         s.repack(last ? 0 : cnt[0], cnt[1]);
-        if (!last) C.bind(s.colptr<float>(Shard::C_BH0), s.colptr<float>(Shard::C_BH1), s.colptr<float>(Shard::C_BL0),
-                          s.colptr<float>(Shard::C_BL1), s.ld_cur);
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        if (!last) C.bind(s.colptr<float>(Shard::C_BH), s.colptr<float>(Shard::C_BL), s.ld_cur);
     }
 }
 
@@ -188,7 +230,10 @@ void dense_run(Shard &s, const admmb_opts *op)
     const int split = getenv("ADMMB_TF32_SINGLE") ? 1 : 3;
     CK(cudaMemsetAsync(D.x.p, 0, sizeof(double) * (size_t)n * s.ld, s.stream));
     // condensed form: only the split rows take part in the per-iteration GEMM (see dense_tf32.cuh)
-    D.condensed = tf32 && !s.has_q && s.nsplitblk > 0 && getenv("ADMMB_NO_CONDENSED") == nullptr;
+    // (needs: no linear cost, states unsplit or not -- every CONTROL block split so the roll-out determines x)
+    bool controls_split = true;
+    for (int k = 0; k < s.N; ++k) controls_split = controls_split && (s.h_bdesc[3 * k + 2] & 0xff) != BLK_NONE;
+    D.condensed = tf32 && !s.has_q && controls_split && getenv("ADMMB_NO_CONDENSED") == nullptr;
     if (D.condensed) {
         dense_run_condensed(s, op, split);
         return;
@@ -203,7 +248,7 @@ void dense_run(Shard &s, const admmb_opts *op)
         k_tf32_split_rows<<<g, 128, 0, s.stream>>>(n, s.ld, D.rt.p, D.tf32.Bhi.p, split == 3 ? D.tf32.Blo.p : nullptr);
         s.launches += 3;
     }
-    DenseStep ds;
+    DenseStep ds{};
     ds.max_iter = op->max_iter;
     ds.reltol = op->reltol;
     ds.sqrtn_abs = sqrt((double)s.nsplit) * op->abstol;

@@ -313,14 +313,19 @@ inline void tf32_launch_gemm(int split, const CUtensorMap &mA, const CUtensorMap
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const unsigned grid = (unsigned)std::min(m_tiles * n_tiles, sms);
-    if (split == 3) {
+    static bool attr_done[64] = {};   // the attribute is per device; set it once, not per launch
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    bool &attr_set = attr_done[cur & 63];
+    if (!attr_set) {
         CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
-        k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
-    } else {
         CK(cudaFuncSetAttribute(k_dense_xupdate_tf32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(1)));
-        k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
+        attr_set = true;
     }
-    CK(cudaGetLastError());
+    if (split == 3)
+        k_dense_xupdate_tf32<3><<<grid, 192, tg_smem_bytes(3), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
+    else
+        k_dense_xupdate_tf32<1><<<grid, 192, tg_smem_bytes(1), st>>>(mA, mAlo, mB, mBlo, n_rows, kpad, ld, m_tiles, n_tiles, X, dbg);
 }
 
 struct Tf32Plan {
@@ -353,147 +358,84 @@ struct Tf32Plan {
     void gemm(cudaStream_t st) { tf32_launch_gemm(split, mA, mAlo, mB, mBlo, n, mpad, kpad, ld, X.p, st, dbg); }
 };
 
-// ---- condensed form ---------------------------------------------------------------------------------
-// When only some rows are split (the control blocks; states are BLK_NONE and there is no linear cost), the
+// ---- condensed incremental form ----------------------------------------------------------------------
+// When the states are unsplit (BLK_NONE), every control block is split and there is no linear cost, the
 // right-hand side is zero outside the split rows R and the prox only reads x on R, so the per-iteration GEMM
-// shrinks to X_R = [M[R,R] | S[R] | mc[R]] * [RT_R; s0; 1] (CW, N = 50: 150+7 instead of 456+7 along both M and
-// K: 9x fewer flops, 3x less traffic).  The full x is produced once, after the loop, by one GEMM with
-// A = [M[:,R] | S | mc].  It needs, per problem, the right-hand side of the iteration the problem finished at:
-// the prox kernel therefore writes the next right-hand side into the OTHER of two buffers (iteration `it` reads
-// buffer (it-1)&1 and writes buffer it&1); a finished problem is never written again, so buffer (iters-1)&1 keeps
-// exactly the right-hand side its final x came from.
+// shrinks to the R x R block of M (CW, N = 50: 153 instead of 456 along both M and K: 9x fewer flops).
+// The x-update is affine in the right-hand side, so the GEMM is applied to its INCREMENT:
+//     x_R^{k+1} = x_R^k + M_RR (rt^k - rt^{k-1}),      x_R^1 from one exact FP64 Riccati x-update,
+// with x_R accumulated in FP64 by the prox kernel.  The TF32/FP32 rounding of the tensor-core product is then
+// relative to the size of the step, which shrinks as ADMM converges, instead of relative to x itself -- the
+// absolute form stalls at |r| ~ 1e-6 |x| and cannot meet a 1e-6 tolerance; the incremental form can.
+// The accumulated x_R only drives the iteration.  When a problem finishes at iteration k, the x it returns is the
+// EXACT FP64 Riccati x-update of the right-hand side its last iteration used, rt^{k-1} = (z^k - u^k) - increment^k
+// (the increment is still in the buffer: a finished problem's column is never written again), so the returned
+// trajectory satisfies the dynamics to FP64 round-off and carries no accumulated tensor-core rounding
+// (k_tf32_final_x in kernels.cuh).
 
-// A[i][k] = M[rmap(i)][cmap[k]] | S[rmap(i)] | mc[rmap(i)]; rmap == nullptr: identity over n rows
-__global__ void k_tf32_pack_factor_cond(int n, int n_out, int nr, int mpad, int kpad, const int *rmap, const int *cmap,
-                                        const double *M, const double *S, const double *mc, float *hi, float *lo)
+// A[i][k] = M[rmap[i]][cmap[k]], zero padded
+__global__ void k_tf32_pack_factor_cond(int n, int nr, int mpad, int kpad, const int *rows, const double *M, float *hi,
+                                        float *lo)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (k >= kpad || i >= mpad) return;
-    double v = 0.0;
-    if (i < n_out) {
-        const int ri = rmap ? rmap[i] : i;
-        v = k < nr ? M[(size_t)ri * n + cmap[k]] : (k < nr + 6 ? S[(size_t)ri * 6 + (k - nr)] : (k == nr + 6 ? mc[ri] : 0.0));
-    }
+    const double v = (i < nr && k < nr) ? M[(size_t)rows[i] * n + rows[k]] : 0.0;
     const float f = (float)v;
     const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
     hi[(size_t)i * kpad + k] = h;
     if (lo) lo[(size_t)i * kpad + k] = (float)(v - (double)h);
 }
 
-// first right-hand side, compact rows: rt[3j+e] = z - u on split block j (z, u are full-row arrays)
-__global__ void k_tf32_rt_init_cond(int nsb, const int *sblk, int64_t batch, size_t ld, const double *z, const double *u,
-                                    float *hi, float *lo)
+// xacc[i][p] = x[rows[i]][p]
+__global__ void k_tf32_gather_rows(int nr, const int *rows, int64_t batch, size_t ld, const double *x, double *xacc)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (p >= batch || j >= nsb) return;
-    const int b = sblk[j];
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-        const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
-        const double t = z[o] - u[o];
-        const float f = (float)t;
-        const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
-        hi[oc] = h;
-        if (lo) lo[oc] = (float)(t - (double)h);
-    }
-}
-
-// per problem, copy the right-hand side its final x was computed from (buffer (iters-1)&1) into the final operand
-__global__ void k_tf32_select_final(int rows, int64_t batch, size_t ld, const int *iters, const float *h0, const float *h1,
-                                    const float *l0, const float *l1, float *hi, float *lo)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (p >= batch || r >= rows) return;
-    const int sel = (iters[p] - 1) & 1;
-    const size_t o = (size_t)r * ld + p;
-    hi[o] = sel ? h1[o] : h0[o];
-    if (lo) lo[o] = sel ? l1[o] : l0[o];
-}
-
-// x_home[r][orig[c]] = (double) xf[r][c] for the finished working-set columns c = fin[t]
-__global__ void k_tf32_scatter_x(int rows, const float *xf, size_t ld_in, const int *fin, int n_fin, const int *orig,
-                                 double *home, size_t ld_home)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_fin) return;
-    const size_t c = (size_t)fin[t], h = orig ? (size_t)orig[c] : c;
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) home[(size_t)r * ld_home + h] = (double)xf[(size_t)r * ld_in + c];
+    const int i = blockIdx.y;
+    if (p < batch && i < nr) xacc[(size_t)i * ld + p] = x[(size_t)rows[i] * ld + p];
 }
 
 struct Tf32Condensed {
-    int n = 0, nr = 0, mpad_r = 0, mpad_n = 0, kpad = 0, split = 1;
+    int n = 0, nr = 0, mpad_r = 0, kpad = 0, split = 1;
     size_t ld = 0, ld_cur = 0;
-    DevBuf<float> Aihi, Ailo, Afhi, Aflo;        // iteration and final factors
-    DevBuf<float> Bhi[2], Blo[2], Bfhi, Bflo;    // ping-pong right-hand sides (home copies), final right-hand side
-    DevBuf<float> Xr, Xf;                        // [mpad_r][ld], [mpad_n][ld]
-    DevBuf<int> rows;                            // R
-    float *bh[2] = {nullptr, nullptr}, *bl[2] = {nullptr, nullptr};   // the buffers of the current working set
-    CUtensorMap mAi, mAilo, mAf, mAflo, mB[2], mBlo[2], mBf, mBflo;
-    void prepare(int n_, const std::vector<int> &R, int64_t batch, size_t ld_, int split_, const double *M, const double *S,
-                 const double *mc, const double *s0, cudaStream_t st)
+    DevBuf<float> Ahi, Alo;          // M_RR
+    DevBuf<float> Bhi, Blo;          // right-hand-side increment (home copy), [kpad][ld]
+    DevBuf<float> Xr;                // M_RR * increment, [mpad_r][ld]
+    DevBuf<double> Xacc;             // accumulated x_R (home copy), [nr][ld]
+    DevBuf<int> rows;                // R
+    float *bh = nullptr, *bl = nullptr;   // the increment buffers of the current working set
+    CUtensorMap mA, mAlo, mB, mBlo;
+    void prepare(int n_, const std::vector<int> &R, size_t ld_, int split_, const double *M, cudaStream_t st)
     {
         n = n_; nr = (int)R.size(); ld = ld_; split = split_;
         mpad_r = (int)round_up((size_t)nr, TG_BM);
-        mpad_n = (int)round_up((size_t)n, TG_BM);
-        kpad = (int)round_up((size_t)nr + 7, 8);
+        kpad = (int)round_up((size_t)nr, 8);
         const bool s3 = split == 3;
         rows.alloc(nr);
         CK(cudaMemcpyAsync(rows.p, R.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, st));
-        Aihi.alloc((size_t)mpad_r * kpad); Afhi.alloc((size_t)mpad_n * kpad);
-        if (s3) { Ailo.alloc((size_t)mpad_r * kpad); Aflo.alloc((size_t)mpad_n * kpad); }
-        dim3 g1((unsigned)((kpad + 127) / 128), (unsigned)mpad_r), g2((unsigned)((kpad + 127) / 128), (unsigned)mpad_n);
-        k_tf32_pack_factor_cond<<<g1, 128, 0, st>>>(n, nr, nr, mpad_r, kpad, rows.p, rows.p, M, S, mc, Aihi.p, s3 ? Ailo.p : nullptr);
-        k_tf32_pack_factor_cond<<<g2, 128, 0, st>>>(n, n, nr, mpad_n, kpad, nullptr, rows.p, M, S, mc, Afhi.p, s3 ? Aflo.p : nullptr);
+        Ahi.alloc((size_t)mpad_r * kpad);
+        if (s3) Alo.alloc((size_t)mpad_r * kpad);
+        dim3 g1((unsigned)((kpad + 127) / 128), (unsigned)mpad_r);
+        k_tf32_pack_factor_cond<<<g1, 128, 0, st>>>(n, nr, mpad_r, kpad, rows.p, M, Ahi.p, s3 ? Alo.p : nullptr);
         CK(cudaGetLastError());
-        auto mk_b = [&](DevBuf<float> &hi, DevBuf<float> &lo) {
-            hi.alloc((size_t)kpad * ld);
-            CK(cudaMemsetAsync(hi.p, 0, sizeof(float) * kpad * ld, st));
-            if (s3) { lo.alloc((size_t)kpad * ld); CK(cudaMemsetAsync(lo.p, 0, sizeof(float) * kpad * ld, st)); }
-            k_tf32_pack_tail<<<(unsigned)((ld + 127) / 128), 128, 0, st>>>(nr, kpad, batch, ld, s0, hi.p, s3 ? lo.p : nullptr);
-            CK(cudaGetLastError());
-        };
-        mk_b(Bhi[0], Blo[0]); mk_b(Bhi[1], Blo[1]);
-        Bfhi.alloc((size_t)kpad * ld);
-        if (s3) Bflo.alloc((size_t)kpad * ld);
+        Bhi.alloc((size_t)kpad * ld);
+        CK(cudaMemsetAsync(Bhi.p, 0, sizeof(float) * kpad * ld, st));       // first increment is zero: x^1 is exact
+        if (s3) { Blo.alloc((size_t)kpad * ld); CK(cudaMemsetAsync(Blo.p, 0, sizeof(float) * kpad * ld, st)); }
         Xr.alloc((size_t)mpad_r * ld);
-        Xf.alloc((size_t)mpad_n * ld);
-        mAi = make_map_2d(Aihi.p, mpad_r, kpad, kpad, TG_BK, TG_BM);
-        mAilo = s3 ? make_map_2d(Ailo.p, mpad_r, kpad, kpad, TG_BK, TG_BM) : mAi;
-        mAf = make_map_2d(Afhi.p, mpad_n, kpad, kpad, TG_BK, TG_BM);
-        mAflo = s3 ? make_map_2d(Aflo.p, mpad_n, kpad, kpad, TG_BK, TG_BM) : mAf;
-        bind(Bhi[0].p, Bhi[1].p, Blo[0].p, Blo[1].p, ld);
+        Xacc.alloc((size_t)nr * ld);
+        mA = make_map_2d(Ahi.p, mpad_r, kpad, kpad, TG_BK, TG_BM);
+        mAlo = s3 ? make_map_2d(Alo.p, mpad_r, kpad, kpad, TG_BK, TG_BM) : mA;
+        bind(Bhi.p, Blo.p, ld);
     }
-    // point the GEMMs at the right-hand-side buffers of the current working set (pitch ld_now)
-    void bind(float *h0, float *h1, float *l0, float *l1, size_t ld_now)
+    // point the GEMM at the increment buffers of the current working set (pitch ld_now)
+    void bind(float *h, float *l, size_t ld_now)
     {
         const bool s3 = split == 3;
         ld_cur = ld_now;
-        bh[0] = h0; bh[1] = h1; bl[0] = s3 ? l0 : nullptr; bl[1] = s3 ? l1 : nullptr;
-        auto map_b = [&](const float *p) { return make_map_2d(p, kpad, ld_cur, ld_cur, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); };
-        for (int i = 0; i < 2; ++i) { mB[i] = map_b(bh[i]); mBlo[i] = s3 ? map_b(bl[i]) : mB[i]; }
-        mBf = map_b(Bfhi.p); mBflo = s3 ? map_b(Bflo.p) : mBf;
+        bh = h; bl = s3 ? l : nullptr;
+        mB = make_map_2d(bh, kpad, ld_cur, ld_cur, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        mBlo = s3 ? make_map_2d(bl, kpad, ld_cur, ld_cur, 32, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : mB;
     }
-    // iteration `it` (1-based): reads buffer (it-1)&1; the prox kernel then writes buffer it&1
-    void gemm_iter(int it, cudaStream_t st)
-    {
-        const int w = (it - 1) & 1;
-        tf32_launch_gemm(split, mAi, mAilo, mB[w], mBlo[w], nr, mpad_r, kpad, ld_cur, Xr.p, st);
-    }
-    // full x of the finished columns fin[0..n_fin) of the working set (width columns), written to their home columns
-    void final_x(int64_t width, const int *iters, const int *fin, int n_fin, const int *orig, double *x_home, size_t ld_home,
-                 cudaStream_t st)
-    {
-        if (n_fin <= 0) return;
-        const bool s3 = split == 3;
-        dim3 g((unsigned)((width + 127) / 128), (unsigned)kpad);   // the tail rows (s0, 1) travel with the buffers
-        k_tf32_select_final<<<g, 128, 0, st>>>(kpad, width, ld_cur, iters, bh[0], bh[1], bl[0], bl[1], Bfhi.p, s3 ? Bflo.p : nullptr);
-        tf32_launch_gemm(split, mAf, mAflo, mBf, mBflo, n, mpad_n, kpad, ld_cur, Xf.p, st);
-        dim3 g2((unsigned)((n_fin + 127) / 128), (unsigned)std::min(n, 64));
-        k_tf32_scatter_x<<<g2, 128, 0, st>>>(n, Xf.p, ld_cur, fin, n_fin, orig, x_home, ld_home);
-        CK(cudaGetLastError());
-    }
+    void gemm(cudaStream_t st) { tf32_launch_gemm(split, mA, mAlo, mB, mBlo, nr, mpad_r, kpad, ld_cur, Xr.p, st); }
 };
 
 }  // namespace admmb

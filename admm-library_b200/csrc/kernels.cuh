@@ -1419,6 +1419,9 @@ __global__ void k_compose_orig(const int *orig_old, const int *src, int n, int *
     if (t < n) orig_new[t] = orig_old ? orig_old[src[t]] : src[t];
 }
 
+__global__ void k_add_int(int *a, int v) { *a += v; }
+__global__ void k_set_int(int *a, int v) { *a = v; }
+
 __global__ void k_iota(int *a, int n)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1636,6 +1639,95 @@ __global__ void k_xupdate_riccati(int N, int64_t batch, size_t ld, const double 
     for (int i = 0; i < 6; ++i) x[(size_t)(9 * N + i) * ld + p] = s[i];
 }
 
+// Retirement of the condensed TF32 path: for the finished working-set columns c = fin[t], x = exact FP64 Riccati
+// x-update (same arithmetic as k_xupdate_riccati) of rt = (z - u) - (inc_hi + inc_lo) on the split rows, zero elsewhere,
+// written to the home column orig[c].  d: scratch [3N][ld_d], one column per t.
+template <bool HAS_C>
+__global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int *__restrict__ bdesc, const double *s0,
+                               const double *z, const double *u, const float *inc_hi, const float *inc_lo, size_t ld_in,
+                               const int *fin, int n_fin, const int *orig, double *d, size_t ld_d, double *home,
+                               size_t ld_home)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_fin) return;
+    const size_t c = (size_t)fin[t], h = orig ? (size_t)orig[c] : c;
+    FacRef<true> F;
+    F.base = fac;
+    F.ld = 0;
+    auto rt = [&](int row) -> double {
+        const int bd = bdesc[row / 3];
+        if ((bd & 0xff) == BLK_NONE) return 0.0;
+        const size_t o = (size_t)row * ld_in + c, oc = (size_t)(3 * (bd >> 8) + row % 3) * ld_in + c;
+        const double inc = (double)inc_hi[oc] + (inc_lo ? (double)inc_lo[oc] : 0.0);
+        return (z[o] - u[o]) - inc;
+    };
+    double g[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = rt(9 * N + i);
+    for (int k = N - 1; k >= 0; --k) {
+        double rs[6], ra[3], pn[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rs[i] = rt(9 * k + i);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ra[j] = rt(9 * k + 6 + j);
+        if (HAS_C) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) g[i] = g[i] - F(k, F_CHAT + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = F(k, F_HINV + HINV_LD * j + 0) * ra[0];
+            acc = fma(F(k, F_HINV + HINV_LD * j + 1), ra[1], acc);
+            acc = fma(F(k, F_HINV + HINV_LD * j + 2), ra[2], acc);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_E + 6 * j + i), g[i], acc);
+            d[(size_t)(3 * k + j) * ld_d + t] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = rs[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_K + 6 * j + i), ra[j], acc);
+#pragma unroll
+            for (int l = 0; l < 6; ++l) acc = fma(F(k, F_ACL + 6 * l + i), g[l], acc);
+            pn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = pn[i];
+    }
+    double s[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = s0[(size_t)i * ld_in + c];
+    for (int k = 0; k < N; ++k) {
+        double a[3], sn[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = d[(size_t)(3 * k + j) * ld_d + t];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
+            a[j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) home[(size_t)(9 * k + i) * ld_home + h] = s[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) home[(size_t)(9 * k + 6 + j) * ld_home + h] = a[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double acc = F(k, F_A + 6 * i + 0) * s[0];
+#pragma unroll
+            for (int l = 1; l < 6; ++l) acc = fma(F(k, F_A + 6 * i + l), s[l], acc);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc = fma(F(k, F_B + B_LD * i + j), a[j], acc);
+            if (HAS_C) acc = acc + F(k, F_C + i);
+            sn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = sn[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) home[(size_t)(9 * N + i) * ld_home + h] = s[i];
+}
+
 // Rows a3 + a4 alone (the streaming prox / dual / residual kernel, "C4"): reads x, z, u once,
 // writes z, u once: 40 bytes per split entry.  All arrays are full-width [n][ld]; BLK_NONE rows are
 // skipped.  Optionally emits the next right-hand side rt = w*(z-u) - q/rho for the dense x-update
@@ -1648,6 +1740,7 @@ struct DenseStep {
     int *iters, *status;       // [ld]
     double *fin;               // [4][ld]
     int *running;              // incremented once per problem still running after this step
+    const int *it_base;        // optional (CUDA-graph replay): iteration number = it + *it_base
 };
 
 // F32: x comes from the TF32 tensor-core GEMM as fp32 and the next right-hand side is written as fp32
@@ -1759,17 +1852,18 @@ __global__ void k_prox_dual_residuals(int nb, int64_t batch, size_t ld, const in
     }
 }
 
-// Condensed TF32 dense path: C3 + C4 + stop test over the split blocks only, several threads per problem.
-// blockDim = (32 problems, CH block-chunks): thread (tx, ty) handles split blocks ty, ty + CH, ... of problem
-// blockIdx.x * 32 + tx, so a warp still touches 32 consecutive problems of one row (coalesced) while the CH
-// warps of a CTA spread the per-problem serial work; the partial norms meet in shared memory and are summed in
-// ascending ty order (deterministic).  x and the right-hand side use compact rows (3j+e for split block j),
-// z, u and par the full rows / block numbers.  The next right-hand side goes to the other ping-pong buffer.
+// Condensed incremental TF32 dense path: C3 + C4 + stop test over the split blocks only, several threads per
+// problem.  blockDim = (32 problems, CH block-chunks): thread (tx, ty) handles split blocks ty, ty + CH, ... of
+// problem blockIdx.x * 32 + tx, so a warp still touches 32 consecutive problems of one row (coalesced) while the
+// CH warps of a CTA spread the per-problem serial work; the partial norms meet in shared memory and are summed
+// in ascending ty order (deterministic).  dx (the tensor-core product M_RR * increment), xacc and the increment
+// use compact rows (3j+e for split block j); z, u and par the full rows / block numbers.
+//   x = xacc + dx (FP64 accumulate),   increment for the next GEMM = (z+ - z) - (u+ - u)
 template <int CH, int MINW>   // MINW: resident warps per SM the register allocation must allow
 __global__ void __launch_bounds__(32 * CH, MINW / CH)
 k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ bdesc, int64_t batch, size_t ld,
-                 const double *par, int par_batched, double alpha, const float *__restrict__ x32, double *z, double *u,
-                 float *rt_hi, float *rt_lo, const DenseStep ds)
+                 const double *par, int par_batched, double alpha, const float *__restrict__ dx32, double *xacc,
+                 double *z, double *u, float *rt_hi, float *rt_lo, const DenseStep ds)
 {
     __shared__ double red[CH][5][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -1784,15 +1878,16 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
         for (int j = ty; j < nsb; j += CH) {
             const int b = sblk[j];
             const int type = bdesc[b] & 0xff;
-            double xb[3], zo[3], v[3], zn[3];
+            double xb[3], zo[3], uo[3], v[3], zn[3];
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                const size_t o = (size_t)(3 * b + e) * ld + p;
-                xb[e] = (double)__ldcs(x32 + (size_t)(3 * j + e) * ld + p);
+                const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
+                xb[e] = ld_stream(xacc + oc) + (double)__ldcs(dx32 + oc);
+                st_stream(xacc + oc, xb[e]);
                 zo[e] = ld_stream(z + o);
-                const double uo = ld_stream(u + o);
+                uo[e] = ld_stream(u + o);
                 const double xh = fma(alpha, xb[e], oma * zo[e]);
-                v[e] = xh + uo;
+                v[e] = xh + uo[e];
             }
             if (par_batched) {
                 const double *pp = par + p + (size_t)(8 * b) * ld;
@@ -1814,7 +1909,7 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
                 uu = fma(un, un, uu);
                 st_stream(z + o, zn[e]);
                 st_stream(u + o, un);
-                const double t = zn[e] - un;
+                const double t = dz - (un - uo[e]);     // increment of z - u: differences of nearby numbers first
                 const float f = (float)t;
                 const float h = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
                 rt_hi[oc] = h;
@@ -1829,6 +1924,7 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
     for (int c = 1; c < CH; ++c) {
         rr += red[c][0][tx]; ss += red[c][1][tx]; xx += red[c][2][tx]; zz += red[c][3][tx]; uu += red[c][4][tx];
     }
+    const int it_now = ds.it + (ds.it_base ? *ds.it_base : 0);
     const double r_norm = sqrt(rr), s_norm = rho * sqrt(ss);
     const double nx = sqrt(xx), nz = sqrt(zz);
     const double eps_pri = fma(ds.reltol, nx > nz ? nx : nz, ds.sqrtn_abs);
@@ -1836,8 +1932,8 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
     int st = ST_RUNNING;
     if (!(isfinite(r_norm) && isfinite(s_norm))) st = ST_NAN;
     else if (r_norm < eps_pri && s_norm < eps_dual) st = ST_CONVERGED;
-    else if (ds.it >= ds.max_iter) st = ST_MAX_ITER;
-    ds.iters[p] = ds.it;
+    else if (it_now >= ds.max_iter) st = ST_MAX_ITER;
+    ds.iters[p] = it_now;
     ds.status[p] = st;
     ds.fin[p] = r_norm;
     ds.fin[p + ld] = s_norm;
