@@ -14,6 +14,7 @@ namespace admmb {
 struct DenseState {
     DevBuf<double> M, S, mc;          // [n][n] row-major, [n][6], [n]
     DevBuf<double> x, rt, norms, dscr; // [n][ld], [n][ld], [5][ld], [3N][ld] (Riccati scratch of the condensed path)
+    DevBuf<double> bf_rt, bf_s0, bf_d, bf_x;   // scratch of dense_build_factor
     DevBuf<int> running, itbase;      // [1], [1] (iteration counter of the graph replays)
     bool ready = false;
     Tf32Plan tf32;                    // tensor-core operands and TMA descriptors (precision = tf32)

@@ -1,5 +1,6 @@
 // dense_impl.cuh -- host side of the dense shared-factor path (included by admm_b200.cu).
 #pragma once
+#include <chrono>
 
 namespace {
 
@@ -11,7 +12,8 @@ void dense_build_factor(Shard &s, const double *fac_dev, bool has_c, double *M, 
     const int n = s.n, N = s.N;
     const int64_t cols = n + 6 + 1;
     const size_t ldc = round_up((size_t)cols, 32);
-    DevBuf<double> rt, s0, d, x;
+    // persistent scratch: cudaMalloc / cudaFree per run cost erratic host time (cudaFree synchronises the device)
+    DevBuf<double> &rt = s.dense.bf_rt, &s0 = s.dense.bf_s0, &d = s.dense.bf_d, &x = s.dense.bf_x;
     rt.alloc((size_t)n * ldc);
     s0.alloc(6 * ldc);
     d.alloc((size_t)3 * N * ldc);
@@ -75,6 +77,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     DenseState &D = s.dense;
     Tf32Condensed &C = D.cond;
     const int n = s.n, nb = s.nb, N = s.N;
+    const auto t_setup0 = std::chrono::steady_clock::now();
     const unsigned gb = (unsigned)((s.batch + 127) / 128);
     std::vector<int> R, sb;
     for (int b = 0; b < nb; ++b)
@@ -95,6 +98,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s.stream));   // R, sb are host temporaries of the async copies above
     s.launches += 4;
+    const double t_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
 
     for (int c = 0; c < Shard::C_COUNT; ++c) s.set_col(c, nullptr, 8, 0, false);
     s.set_col(Shard::C_Z, s.z.p, 8, n, true);
@@ -120,11 +124,21 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     ds.running = D.running.p;
     int chunk = op->chunk > 0 ? op->chunk : 25;
     const int chunk_max = op->chunk > 0 ? op->chunk : 200;
-    constexpr int GRAPH_ITERS = 20;
+    constexpr int GRAPH_ITERS = 10;
     const bool use_graphs = getenv("ADMMB_NO_GRAPH") == nullptr;
     cudaGraphExec_t gexec = nullptr;
+    bool gstale = false;
     struct GraphGuard { cudaGraphExec_t &g; ~GraphGuard() { if (g) cudaGraphExecDestroy(g); } } guard{gexec};
     D.itbase.alloc(1);
+    // ADMMB_TRACE: host time per section of the loop (the GPU idles while the host works between chunks)
+    const bool trace = getenv("ADMMB_TRACE") != nullptr;
+    double t_sec[6] = {0, 0, 0, 0, 0, 0};   // launch, graph build, split+sync, final x, repack, bind
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const int refresh = getenv("ADMMB_TF32_REFRESH") ? atoi(getenv("ADMMB_TF32_REFRESH")) : 1000;
+    int last_refresh = 0;
     int it = 0;
     while (s.width > 0 && it < op->max_iter) {
         const int64_t width = s.width;
@@ -142,6 +156,18 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         if (const char *e = getenv("ADMMB_PROX_W")) pw = atoi(e);
         const unsigned gc = (unsigned)((width + 31) / 32);
         const int steps = std::min(chunk, op->max_iter - it);
+        // every `refresh` iterations: x_R = exact FP64 x-update of the current (z, u), increment = 0 (drops the
+        // rounding the tensor-core increments have accumulated in x_R)
+        if (refresh > 0 && it - last_refresh >= refresh) {
+            const unsigned gr = (unsigned)((width + 63) / 64);
+            const double *s0w = s.colptr<double>(Shard::C_S0);
+            if (s.has_c) k_tf32_final_x<true, true><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, s.ld, xacc, s.ld_cur, ds.status);
+            else k_tf32_final_x<false, true><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, s.ld, xacc, s.ld_cur, ds.status);
+            k_tf32_zero_running<<<dim3((unsigned)((width + 127) / 128), (unsigned)C.kpad), 128, 0, s.stream>>>(C.kpad, width, s.ld_cur, ds.status, C.bh, C.bl);
+            CK(cudaGetLastError());
+            s.launches += 2;
+            last_refresh = it;
+        }
         s.trace_active.push_back((int)width);
         auto launch_iter = [&](const DenseStep &d) {
             C.gemm(s.stream);
@@ -155,12 +181,14 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
             s.launches += 2;
         };
         s.kernel_tic();
+        auto tl0 = now();
         int k = 0;
         // long chunks replay a captured graph of GRAPH_ITERS iterations (2 launches each): the loop is launch-bound
         // at small widths; the iteration number then comes from a device counter.  The graph bakes in the pointers
         // of the current working set, so it is dropped at every repack.
-        if (use_graphs && steps >= 2 * GRAPH_ITERS) {
-            if (!gexec) {
+        if (use_graphs && steps >= GRAPH_ITERS) {
+            if (!gexec || gstale) {
+                auto tg0 = now();
                 cudaGraph_t g = nullptr;
                 DenseStep dg = ds;
                 dg.it_base = D.itbase.p;
@@ -168,9 +196,19 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
                 for (int q = 1; q <= GRAPH_ITERS; ++q) { dg.it = q; launch_iter(dg); }
                 k_add_int<<<1, 1, 0, s.stream>>>(D.itbase.p, GRAPH_ITERS);
                 CK(cudaStreamEndCapture(s.stream, &g));
-                CK(cudaGraphInstantiate(&gexec, g, 0));
-                cudaGraphDestroy(g);
                 s.launches -= 2 * GRAPH_ITERS;   // captured, not launched
+                // same topology as before a repack, new pointers / grids: update the executable in place
+                // (re-instantiating costs far more host time); fall back to a fresh instantiation if refused
+                bool ok = false;
+                if (gexec) {
+                    cudaGraphExecUpdateResultInfo info;
+                    ok = cudaGraphExecUpdate(gexec, g, &info) == cudaSuccess;
+                    if (!ok) { (void)cudaGetLastError(); cudaGraphExecDestroy(gexec); gexec = nullptr; }
+                }
+                if (!ok) CK(cudaGraphInstantiate(&gexec, g, 0));
+                cudaGraphDestroy(g);
+                gstale = false;
+                t_sec[1] += since(tg0);
             }
             k_set_int<<<1, 1, 0, s.stream>>>(D.itbase.p, it);
             for (; steps - k >= GRAPH_ITERS; k += GRAPH_ITERS, it += GRAPH_ITERS) {
@@ -184,6 +222,8 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
             launch_iter(ds);
         }
         s.kernel_toc();
+        t_sec[0] += since(tl0);
+        auto ts0 = now();
         CK(cudaGetLastError());
         // who is still running?
         CK(cudaMemsetAsync(s.split_counts.p, 0, 2 * sizeof(int), s.stream));
@@ -193,6 +233,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         int cnt[2] = {0, 0};
         CK(cudaMemcpyAsync(cnt, s.split_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
+        t_sec[2] += since(ts0);
         if (op->chunk <= 0) {   // same launch-length policy as the Riccati path: <= ~2 % of the set finishing per check
             const int prev = chunk;
             if (cnt[1] == 0) chunk = std::min(chunk * 2, chunk_max);
@@ -204,18 +245,27 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         // iterations' worth of traffic); a finished problem's columns are never written again, so retiring it later
         // is safe
         if (!last && (no_repack || (int64_t)cnt[1] * 32 < width)) continue;
+        auto tf0 = now();
         {
             const unsigned gf = (unsigned)((cnt[1] + 63) / 64);
             const int *orig = s.cur_set < 0 ? nullptr : s.orig[s.cur_set].p;
             const double *s0w = s.colptr<double>(Shard::C_S0);
-            if (s.has_c) k_tf32_final_x<true><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld);
-            else k_tf32_final_x<false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld);
+            if (s.has_c) k_tf32_final_x<true, false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld, nullptr);
+            else k_tf32_final_x<false, false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld, nullptr);
             ++s.launches;
         }
+        t_sec[3] += since(tf0);
+        auto tr0 = now();
         s.repack(last ? 0 : cnt[0], cnt[1]);
-        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        t_sec[4] += since(tr0);
+        gstale = true;
+        auto tb0 = now();
         if (!last) C.bind(s.colptr<float>(Shard::C_BH), s.colptr<float>(Shard::C_BL), s.ld_cur);
+        t_sec[5] += since(tb0);
     }
+    if (trace)
+        fprintf(stderr, "[admmb trace] dense host ms: setup %.1f launch %.1f (graph build %.1f) split+sync %.1f final-x %.1f repack %.1f bind %.1f\n",
+                t_setup, t_sec[0], t_sec[1], t_sec[2], t_sec[3], t_sec[4], t_sec[5]);
 }
 
 void dense_run(Shard &s, const admmb_opts *op)

@@ -394,6 +394,16 @@ __global__ void k_tf32_gather_rows(int nr, const int *rows, int64_t batch, size_
     if (p < batch && i < nr) xacc[(size_t)i * ld + p] = x[(size_t)rows[i] * ld + p];
 }
 
+// increment = 0 for the still-running columns (after a refresh of x_R)
+__global__ void k_tf32_zero_running(int rows, int64_t width, size_t ld, const int *status, float *hi, float *lo)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (p >= width || r >= rows || status[p] != ST_RUNNING) return;
+    hi[(size_t)r * ld + p] = 0.f;
+    if (lo) lo[(size_t)r * ld + p] = 0.f;
+}
+
 struct Tf32Condensed {
     int n = 0, nr = 0, mpad_r = 0, kpad = 0, split = 1;
     size_t ld = 0, ld_cur = 0;

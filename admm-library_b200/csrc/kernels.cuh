@@ -1642,15 +1642,24 @@ __global__ void k_xupdate_riccati(int N, int64_t batch, size_t ld, const double 
 // Retirement of the condensed TF32 path: for the finished working-set columns c = fin[t], x = exact FP64 Riccati
 // x-update (same arithmetic as k_xupdate_riccati) of rt = (z - u) - (inc_hi + inc_lo) on the split rows, zero elsewhere,
 // written to the home column orig[c].  d: scratch [3N][ld_d], one column per t.
-template <bool HAS_C>
+// REFRESH: the same solve for every working-set column (fin == nullptr, no increment subtracted: rt = z - u is the
+// right-hand side of the NEXT iteration), written to the split rows of the accumulated x_R (home = xacc, pitch
+// ld_home = ld_in) -- removes the rounding accumulated so far; the caller then zeroes the increment buffers.
+template <bool HAS_C, bool REFRESH>
 __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int *__restrict__ bdesc, const double *s0,
                                const double *z, const double *u, const float *inc_hi, const float *inc_lo, size_t ld_in,
                                const int *fin, int n_fin, const int *orig, double *d, size_t ld_d, double *home,
-                               size_t ld_home)
+                               size_t ld_home, const int *status)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_fin) return;
-    const size_t c = (size_t)fin[t], h = orig ? (size_t)orig[c] : c;
+    if (REFRESH && status[t] != ST_RUNNING) return;     // finished columns keep the x_R of their last iteration
+    const size_t c = REFRESH ? (size_t)t : (size_t)fin[t], h = REFRESH ? c : (orig ? (size_t)orig[c] : c);
+    auto put = [&](int row, double v) {
+        if (!REFRESH) { home[(size_t)row * ld_home + h] = v; return; }
+        const int bd = bdesc[row / 3];
+        if ((bd & 0xff) != BLK_NONE) home[(size_t)(3 * (bd >> 8) + row % 3) * ld_home + h] = v;
+    };
     FacRef<true> F;
     F.base = fac;
     F.ld = 0;
@@ -1658,6 +1667,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
         const int bd = bdesc[row / 3];
         if ((bd & 0xff) == BLK_NONE) return 0.0;
         const size_t o = (size_t)row * ld_in + c, oc = (size_t)(3 * (bd >> 8) + row % 3) * ld_in + c;
+        if (REFRESH) return z[o] - u[o];
         const double inc = (double)inc_hi[oc] + (inc_lo ? (double)inc_lo[oc] : 0.0);
         return (z[o] - u[o]) - inc;
     };
@@ -1708,9 +1718,9 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
             a[j] = acc;
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) home[(size_t)(9 * k + i) * ld_home + h] = s[i];
+        for (int i = 0; i < 6; ++i) put(9 * k + i, s[i]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) home[(size_t)(9 * k + 6 + j) * ld_home + h] = a[j];
+        for (int j = 0; j < 3; ++j) put(9 * k + 6 + j, a[j]);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             double acc = F(k, F_A + 6 * i + 0) * s[0];
@@ -1725,7 +1735,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
         for (int i = 0; i < 6; ++i) s[i] = sn[i];
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) home[(size_t)(9 * N + i) * ld_home + h] = s[i];
+    for (int i = 0; i < 6; ++i) put(9 * N + i, s[i]);
 }
 
 // Rows a3 + a4 alone (the streaming prox / dual / residual kernel, "C4"): reads x, z, u once,

@@ -332,3 +332,27 @@ def test_tf32_incremental_reaches_fp64_tolerance(solver, cpu_oracle, P):
     s_next = np.concatenate([s[:, 1:], x[:, 9 * N:].reshape(-1, 1, 6)], axis=1)
     res = s_next - np.einsum("kij,pkj->pki", A, s) - np.einsum("kij,pkj->pki", B, a)
     assert np.abs(res).max() <= 1e-12 * sx
+
+
+@pytest.mark.gpu
+def test_tf32_incremental_reaches_1e8_where_absolute_form_stalls(solver, P):
+    """Tolerance 1e-8: the incremental form (with its periodic exact refresh of x_R) converges like the FP64 Riccati
+    path; the absolute TF32x3 form (ADMMB_NO_CONDENSED=1: X = M RT on the tensor cores) stalls on its ~1e-6 |x|
+    rounding floor.  scripts/tf32_tolerance_sweep.py prints the full table."""
+    import os
+    prob, opts = P.cfg2_cw_batch(batch=128, N=50, seed=11)
+    o = dict(opts, abstol=1e-8, reltol=1e-8, max_iter=40000)
+    ref = solver.solve(prob, o)[3]
+    inc = solver.solve(prob, dict(o, xupdate="dense", precision="tf32"))[3]
+    os.environ["ADMMB_NO_CONDENSED"] = "1"
+    try:
+        ab = solver.solve(prob, dict(o, xupdate="dense", precision="tf32"))[3]
+    finally:
+        del os.environ["ADMMB_NO_CONDENSED"]
+    n_ref, n_inc, n_abs = [(h["status"] == 0).sum() for h in (ref, inc, ab)]
+    assert n_ref > 0.6 * 128
+    assert abs(int(n_inc) - int(n_ref)) <= 4
+    assert n_abs < 0.2 * n_ref
+    both = (ref["status"] == 0) & (inc["status"] == 0)
+    ratio = inc["iters"][both].astype(float) / ref["iters"][both]
+    assert 0.97 < np.median(ratio) < 1.03
