@@ -150,7 +150,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         double *xacc = s.colptr<double>(Shard::C_XACC);
         const double *par = s.par_batched ? s.colptr<double>(Shard::C_PAR) : s.par.p;
         // threads per problem of the prox kernel: enough CTAs x warps to fill the GPU at small widths
-        int ch = width >= 32768 ? 4 : (width >= 8192 ? 8 : 16);
+        int ch = width >= 32768 ? 4 : (width >= 8192 ? 8 : (width >= 2048 ? 16 : 32));
         int pw = ch == 16 ? 16 : (ch == 8 ? 24 : 32);
         if (const char *e = getenv("ADMMB_PROX_CH")) ch = atoi(e);
         if (const char *e = getenv("ADMMB_PROX_W")) pw = atoi(e);
@@ -176,7 +176,8 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
                                                                s.par_batched, op->alpha, C.Xr.p, xacc, z, u, C.bh, C.bl, d)
             if (ch == 4) { if (pw == 16) ADMMB_PROX_COND(4, 16); else if (pw == 24) ADMMB_PROX_COND(4, 24); else ADMMB_PROX_COND(4, 32); }
             else if (ch == 8) { if (pw == 16) ADMMB_PROX_COND(8, 16); else if (pw == 24) ADMMB_PROX_COND(8, 24); else ADMMB_PROX_COND(8, 32); }
-            else { if (pw == 16) ADMMB_PROX_COND(16, 16); else ADMMB_PROX_COND(16, 32); }
+            else if (ch == 16) { if (pw == 16) ADMMB_PROX_COND(16, 16); else ADMMB_PROX_COND(16, 32); }
+            else ADMMB_PROX_COND(32, 32);
 #undef ADMMB_PROX_COND
             s.launches += 2;
         };
