@@ -175,6 +175,28 @@ def test_two_gpus_in_one_process_match_one_gpu(pkg, cpu_oracle, P):
     assert_bit_identical(got, ref, "two GPUs, one process")
     assert got[3]["stats"][:3] == [int(v) for v in ref[3]["stats"][:3]]
 
+def test_two_gpus_in_one_process_tf32_path(pkg, solver, P):
+    """The tensor-core path under the in-process two-GPU deployment: each worker thread captures and replays its own
+    CUDA graphs and sets its own device's kernel attributes.  Unlike the FP64 path this one is NOT invariant to how
+    the batch is sharded (the number of threads per problem -- hence the summation order of the norms -- and the
+    iteration at which x_R is refreshed depend on the width of the working set), so the comparison with the one-GPU
+    run is within the path's precision class, not bitwise."""
+    try:
+        s2 = pkg.Solver(devices=[0, 1])
+    except pkg.AdmmError:
+        pytest.skip("needs two visible GPUs")
+    prob, opts = P.cfg2_cw_batch(batch=700, N=20, seed=21)
+    opts = dict(opts, max_iter=3000, abstol=1e-5, reltol=1e-5, xupdate="dense", precision="tf32")
+    got = s2.solve(prob, opts)
+    s2.close()
+    one = solver.solve(prob, opts)
+    assert (got[3]["status"] == 0).mean() > 0.5 and len(np.unique(got[3]["iters"])) > 20
+    np.testing.assert_array_equal(got[3]["status"], one[3]["status"])
+    di = np.abs(got[3]["iters"].astype(int) - one[3]["iters"].astype(int))
+    assert (di == 0).mean() > 0.9 and di.max() <= 0.05 * one[3]["iters"].max()
+    sx = np.abs(one[0]).max()
+    assert np.abs(got[0] - one[0]).max() <= 5e-3 * sx and np.abs(got[1] - one[1]).max() <= 5e-3 * sx
+
 
 @pytest.mark.parametrize("seed", range(12))
 def test_random_problem_shapes(solver, cpu_oracle, P, seed):
