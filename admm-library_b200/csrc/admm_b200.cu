@@ -33,6 +33,7 @@ thread_local std::string g_create_error;
 struct Shard;
 void dense_prepare(Shard &s, const admmb_opts *op);
 void dense_run(Shard &s, const admmb_opts *op);
+void dense_tail(Shard &s, const admmb_opts *op, int it0);
 void dense_output(Shard &s, double *xo, double *zo, double *uo);
 void dense_tf32_xupdate(Shard &s);
 int dense_tf32_unit(Shard &s, int n, int64_t batch, size_t ld, const double *M, const double *S, const double *mc,
@@ -84,6 +85,8 @@ struct Shard {
          q_batched = false, par_batched = false, has_z0 = false, has_u0 = false, has_rho0 = false;
     bool shared_factor = true, uploaded = false, ran = false;
     bool use_dense = false;
+    bool tf32_tail = false;           // precision = tf32 with xupdate = auto: Riccati kernel while the working set is wide,
+                                      // condensed incremental tensor-core pair once it is narrow (dense_tail)
     bool fast_pattern = false;   // stage states unsplit, every control split: prefetching kernel variant
     bool decoupled = false;      // in-plane / cross-track structure proven on the factor: packed records
     int max_iter_alloc = 0;
@@ -99,6 +102,7 @@ struct Shard {
            C_RAWC, C_RAWQ, C_RAWR, C_XACC, C_BH, C_BL, C_COUNT };
     struct ColArray {
         void *home = nullptr;
+        void *cur_override = nullptr;   // array created mid-run at the current pitch: stands in for work[cur_set] until the next repack
         size_t elem = 8;
         int rows = 0;          // 0: array absent / shared (does not travel)
         bool retire = false;   // written by the solver: finished problems copy it back to their home column
@@ -113,12 +117,14 @@ struct Shard {
     T *colptr(int c) const
     {
         const ColArray &a = cols[c];
+        if (a.cur_override) return (T *)a.cur_override;
         if (a.rows == 0 || cur_set < 0) return (T *)a.home;
         return (T *)a.work[cur_set].p;
     }
     void set_col(int c, void *home, size_t elem, int rows, bool retire)
     {
         cols[c].home = home; cols[c].elem = elem; cols[c].rows = home ? rows : 0; cols[c].retire = retire;
+        cols[c].cur_override = nullptr;
     }
     void repack(int n_keep, int n_fin);
     DevBuf<unsigned long long> counters;   // [0] refactor count, [1] converged, [2] sum iters, [3] max iters
@@ -231,6 +237,12 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     const bool has_P = has_Q || has_R;
     const bool per_rho = op->adapt_rho || has_rho0;
     shared_factor = !dyn_batched && (!has_P || !per_rho);
+    {
+        bool controls_split = true;
+        for (int k = 0; k < N; ++k) controls_split = controls_split && pb->block_type[3 * k + 2] != BLK_NONE;
+        tf32_tail = op->precision == ADMMB_PREC_TF32 && op->xupdate == ADMMB_XUPDATE_AUTO && shared_factor && !has_q &&
+                    controls_split && !op->adapt_rho && !op->history && getenv("ADMMB_NO_TF32_TAIL") == nullptr;
+    }
 
     // raw model
     const size_t md = dyn_batched ? ld : 1;
@@ -336,7 +348,8 @@ void Shard::repack(int n_keep, int n_fin)
         ColArray &a = cols[c];
         if (a.rows == 0) continue;
         a.work[nxt].alloc((size_t)a.rows * ld_new * a.elem);
-        const void *src = cur_set < 0 ? a.home : (const void *)a.work[cur_set].p;
+        const void *src = a.cur_override ? a.cur_override : (cur_set < 0 ? a.home : (const void *)a.work[cur_set].p);
+        a.cur_override = nullptr;
         dim3 grid(gk, rows_grid(a.rows));
         if (a.elem == 8)
             k_gather_cols<double><<<grid, 128, 0, stream>>>((const double *)src, ld_cur, a.rows, keep_list.p, n_keep,
@@ -443,6 +456,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
 
         // which per-problem arrays travel with the working set
         const bool refac = !shared_factor && has_P && adapt;
+        for (int c = 0; c < C_COUNT; ++c) set_col(c, nullptr, 8, 0, false);   // incl. what a previous run's tail registered
         set_col(C_Z, z.p, 8, rows_zu, true);
         set_col(C_U, u.p, 8, rows_zu, true);
         set_col(C_D, d.p, 8, 3 * N, true);
@@ -469,8 +483,11 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         // launches get longer once few problems finish per launch: the host round trip (split, count
         // read-back, repack) then costs relatively less and nothing is lost in early-exit granularity
         const int chunk_max = op->chunk > 0 ? op->chunk : 400;
+        // below this many running problems one warp's serial sweep bounds the Riccati kernel (~42 us per iteration)
+        // and the GEMM + prox pair is faster
+        const int64_t tail_width = getenv("ADMMB_TF32_SWITCH") ? atoll(getenv("ADMMB_TF32_SWITCH")) : 12288;
         int done_iters = 0;
-        while (width > 0 && done_iters < op->max_iter) {
+        while (width > 0 && done_iters < op->max_iter && !(tf32_tail && width <= tail_width)) {
             P.chunk = chunk;
             P.ld = ld_cur;
             P.n_active = (int)width;
@@ -516,7 +533,10 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             if (cnt[0] == (int)width) continue;                 // nobody finished in this launch
             if (no_repack && cnt[0] > 0 && cur_set < 0) continue;   // debug: finished lanes just idle
             repack(cnt[0], cnt[1]);
+            if (tf32_tail && width > 0 && width <= tail_width) break;
         }
+        // precision = tf32, xupdate = auto: the narrow remainder continues on the tensor-core pair
+        if (tf32_tail && width > 0 && width <= tail_width && done_iters < op->max_iter) dense_tail(*this, op, done_iters);
         if (width > 0 && cur_set >= 0) {   // max_iter reached between checks: everything left is final
             CK(cudaMemsetAsync(split_counts.p, 0, 2 * sizeof(int), stream));
             k_iota<<<(unsigned)((width + 127) / 128), 128, 0, stream>>>(fin_list.p, (int)width);
@@ -657,8 +677,10 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
         return fail(h, ADMMB_E_BADARG, "adaptive rho needs mu > 1, tau > 1, every >= 1");
     if (op->xupdate < 0 || op->xupdate > 2) return fail(h, ADMMB_E_BADARG, "xupdate must be an ADMMB_XUPDATE_* code");
     if (op->precision != ADMMB_PREC_FP64 && op->precision != ADMMB_PREC_TF32) return fail(h, ADMMB_E_BADARG, "bad precision");
-    if (op->precision == ADMMB_PREC_TF32 && op->xupdate != ADMMB_XUPDATE_DENSE)
-        return fail(h, ADMMB_E_BADARG, "TF32 applies to the dense x-update only");
+    // TF32 + dense: the tensor-core path throughout; TF32 + auto: tensor cores are allowed where they are faster
+    // (narrow working sets, eligible problems; otherwise the FP64 Riccati kernel runs)
+    if (op->precision == ADMMB_PREC_TF32 && op->xupdate == ADMMB_XUPDATE_RICCATI)
+        return fail(h, ADMMB_E_BADARG, "TF32 does not apply to xupdate = riccati (use dense or auto)");
     if (op->xupdate == ADMMB_XUPDATE_DENSE) {
         const bool has_P = pb->Q || pb->R;
         if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
@@ -781,7 +803,7 @@ int admmb_upload(admmb_handle h, const admmb_problem *pb, const admmb_opts *op)
             Shard &s = h->shards[g];
             if (g >= G || c <= 0) { s.uploaded = false; s.batch = 0; return; }
             s.upload(pb, op, b, c);
-            if (s.use_dense) dense_prepare(s, op);
+            if (s.use_dense || s.tf32_tail) dense_prepare(s, op);
         });
         return (int)ADMMB_OK;
     });

@@ -64,7 +64,7 @@ void dense_prepare(Shard &s, const admmb_opts *)
     D.M.alloc((size_t)s.n * s.n);
     D.S.alloc((size_t)s.n * 6);
     D.mc.alloc(s.n);
-    D.x.alloc((size_t)s.n * s.ld);
+    if (s.use_dense) D.x.alloc((size_t)s.n * s.ld);
     D.running.alloc(1);
     D.ready = false;
 }
@@ -72,6 +72,15 @@ void dense_prepare(Shard &s, const admmb_opts *)
 // The condensed incremental TF32 loop (see dense_tf32.cuh) with physical compaction: the still-running problems
 // travel in a dense, 32-aligned working set (the same ColArray machinery as the Riccati path: z, u, x_R, s0, rho,
 // iters, status, fin, par and the increment buffers); a finished problem's full x is computed when it retires.
+void condensed_loop(Shard &s, const admmb_opts *op, int split, int it0, bool tail, double t_setup);
+
+// the split rows R and the list of split blocks
+static void condensed_rows(Shard &s, std::vector<int> &R, std::vector<int> &sb)
+{
+    for (int b = 0; b < s.nb; ++b)
+        if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
+}
+
 void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
 {
     DenseState &D = s.dense;
@@ -80,8 +89,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     const auto t_setup0 = std::chrono::steady_clock::now();
     const unsigned gb = (unsigned)((s.batch + 127) / 128);
     std::vector<int> R, sb;
-    for (int b = 0; b < nb; ++b)
-        if ((s.h_bdesc[b] & 0xff) != BLK_NONE) { sb.push_back(b); for (int e = 0; e < 3; ++e) R.push_back(3 * b + e); }
+    condensed_rows(s, R, sb);
     D.sblk.alloc(sb.size());
     CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
     C.prepare(n, R, s.ld, split, D.M.p, s.stream);
@@ -115,6 +123,46 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     s.cur_set = -1;
     s.width = s.batch;
     s.ld_cur = s.ld;
+    condensed_loop(s, op, split, 0, false, t_setup);
+}
+
+// precision = tf32, xupdate = auto: the Riccati loop hands over its working set (compact z / u rows, d, s0, rho,
+// iters, status, fin, par already travelling) once it is narrow.  x_R starts from an exact FP64 x-update of the
+// current (z, u); a finished problem leaves its d (backward-sweep result of its last right-hand side) in the
+// working set, from which the Riccati path's k_output recomputes x at download exactly as for the other problems.
+void dense_tail(Shard &s, const admmb_opts *op, int it0)
+{
+    DenseState &D = s.dense;
+    Tf32Condensed &C = D.cond;
+    const auto t_setup0 = std::chrono::steady_clock::now();
+    const int split = getenv("ADMMB_TF32_SINGLE") ? 1 : 3;
+    std::vector<int> R, sb;
+    condensed_rows(s, R, sb);
+    dense_build_factor(s, s.fac.p, s.has_c, D.M.p, D.S.p, D.mc.p);
+    D.sblk.alloc(sb.size());
+    CK(cudaMemcpyAsync(D.sblk.p, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, s.stream));
+    C.prepare(s.n, R, s.ld_cur, split, D.M.p, s.stream);      // buffers at the pitch of the current working set
+    D.dscr.alloc((size_t)3 * s.N * s.ld_cur);
+    CK(cudaStreamSynchronize(s.stream));
+    s.set_col(Shard::C_XACC, C.Xacc.p, 8, C.nr, false);
+    s.set_col(Shard::C_BH, C.Bhi.p, 4, C.kpad, false);
+    s.set_col(Shard::C_BL, split == 3 ? C.Blo.p : nullptr, 4, C.kpad, false);
+    s.cols[Shard::C_XACC].cur_override = C.Xacc.p;
+    s.cols[Shard::C_BH].cur_override = C.Bhi.p;
+    if (split == 3) s.cols[Shard::C_BL].cur_override = C.Blo.p;
+    const double t_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
+    condensed_loop(s, op, split, it0, true, t_setup);
+}
+
+// tail = false: z / u are full-row arrays, x_R is initialised by the caller, finished problems get their full x in D.x
+// tail = true : z / u use the Riccati path's compact rows, x_R is initialised here from (z, u), finished problems
+//               leave d in the working set
+void condensed_loop(Shard &s, const admmb_opts *op, int split, int it0, bool tail, double t_setup)
+{
+    DenseState &D = s.dense;
+    Tf32Condensed &C = D.cond;
+    const int nb = s.nb, N = s.N;
+    (void)nb;
     const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
 
     DenseStep ds{};
@@ -130,6 +178,7 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
     bool gstale = false;
     struct GraphGuard { cudaGraphExec_t &g; ~GraphGuard() { if (g) cudaGraphExecDestroy(g); } } guard{gexec};
     D.itbase.alloc(1);
+    const size_t dscr_ld = D.dscr.n / (size_t)(3 * N);      // pitch of the Riccati scratch
     // ADMMB_TRACE: host time per section of the loop (the GPU idles while the host works between chunks)
     const bool trace = getenv("ADMMB_TRACE") != nullptr;
     double t_sec[6] = {0, 0, 0, 0, 0, 0};   // launch, graph build, split+sync, final x, repack, bind
@@ -138,8 +187,13 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     const int refresh = getenv("ADMMB_TF32_REFRESH") ? atoi(getenv("ADMMB_TF32_REFRESH")) : 1000;
-    int last_refresh = 0;
-    int it = 0;
+    const int zu_compact = tail ? 1 : 0;
+    // the tail starts with a "refresh": x_R = exact x-update of the (z, u) the Riccati loop left, increment = 0
+    // refresh schedule: early and often while the steps are large (that is where the increments' rounding accumulates:
+    // it is relative to the step), then every `refresh` iterations
+    int next_refresh = refresh > 0 ? it0 + 64 : 0x7fffffff;
+    bool force_refresh = tail;
+    int it = it0;
     while (s.width > 0 && it < op->max_iter) {
         const int64_t width = s.width;
         ds.rho = s.colptr<double>(Shard::C_RHO);
@@ -158,22 +212,23 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
         const int steps = std::min(chunk, op->max_iter - it);
         // every `refresh` iterations: x_R = exact FP64 x-update of the current (z, u), increment = 0 (drops the
         // rounding the tensor-core increments have accumulated in x_R)
-        if (refresh > 0 && it - last_refresh >= refresh) {
+        if (force_refresh || it >= next_refresh) {
+            force_refresh = false;
+            if (refresh > 0) next_refresh = (it - it0 < 512) ? it0 + 2 * std::max(it - it0, 32) : it + refresh;
             const unsigned gr = (unsigned)((width + 63) / 64);
             const double *s0w = s.colptr<double>(Shard::C_S0);
-            if (s.has_c) k_tf32_final_x<true, true><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, s.ld, xacc, s.ld_cur, ds.status);
-            else k_tf32_final_x<false, true><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, s.ld, xacc, s.ld_cur, ds.status);
+            if (s.has_c) k_tf32_final_x<true, 1><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, zu_compact, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, dscr_ld, xacc, s.ld_cur, ds.status);
+            else k_tf32_final_x<false, 1><<<gr, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, zu_compact, nullptr, nullptr, s.ld_cur, nullptr, (int)width, nullptr, D.dscr.p, dscr_ld, xacc, s.ld_cur, ds.status);
             k_tf32_zero_running<<<dim3((unsigned)((width + 127) / 128), (unsigned)C.kpad), 128, 0, s.stream>>>(C.kpad, width, s.ld_cur, ds.status, C.bh, C.bl);
             CK(cudaGetLastError());
             s.launches += 2;
-            last_refresh = it;
         }
         s.trace_active.push_back((int)width);
         auto launch_iter = [&](const DenseStep &d) {
             C.gemm(s.stream);
 #define ADMMB_PROX_COND(CH, W)                                                                                           \
     k_prox_cond_tf32<CH, W><<<gc, dim3(32, CH), 0, s.stream>>>(s.nsplitblk, D.sblk.p, s.bdesc.p, width, s.ld_cur, par,  \
-                                                               s.par_batched, op->alpha, C.Xr.p, xacc, z, u, C.bh, C.bl, d)
+                                                               s.par_batched, op->alpha, C.Xr.p, xacc, z, u, zu_compact, C.bh, C.bl, d)
             if (ch == 4) { if (pw == 16) ADMMB_PROX_COND(4, 16); else if (pw == 24) ADMMB_PROX_COND(4, 24); else ADMMB_PROX_COND(4, 32); }
             else if (ch == 8) { if (pw == 16) ADMMB_PROX_COND(8, 16); else if (pw == 24) ADMMB_PROX_COND(8, 24); else ADMMB_PROX_COND(8, 32); }
             else if (ch == 16) { if (pw == 16) ADMMB_PROX_COND(16, 16); else ADMMB_PROX_COND(16, 32); }
@@ -251,8 +306,14 @@ void dense_run_condensed(Shard &s, const admmb_opts *op, int split)
             const unsigned gf = (unsigned)((cnt[1] + 63) / 64);
             const int *orig = s.cur_set < 0 ? nullptr : s.orig[s.cur_set].p;
             const double *s0w = s.colptr<double>(Shard::C_S0);
-            if (s.has_c) k_tf32_final_x<true, false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld, nullptr);
-            else k_tf32_final_x<false, false><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, s.ld, D.x.p, s.ld, nullptr);
+            if (tail) {   // leave d of the last right-hand side in the working set; k_output rebuilds x at download
+                double *dw = s.colptr<double>(Shard::C_D);
+                if (s.has_c) k_tf32_final_x<true, 2><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, 1, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], nullptr, dw, s.ld_cur, nullptr, 0, nullptr);
+                else k_tf32_final_x<false, 2><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, 1, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], nullptr, dw, s.ld_cur, nullptr, 0, nullptr);
+            } else {
+                if (s.has_c) k_tf32_final_x<true, 0><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, 0, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, dscr_ld, D.x.p, s.ld, nullptr);
+                else k_tf32_final_x<false, 0><<<gf, 64, 0, s.stream>>>(N, s.fac.p, s.bdesc.p, s0w, z, u, 0, C.bh, C.bl, s.ld_cur, s.fin_list.p, cnt[1], orig, D.dscr.p, dscr_ld, D.x.p, s.ld, nullptr);
+            }
             ++s.launches;
         }
         t_sec[3] += since(tf0);

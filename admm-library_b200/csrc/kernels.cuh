@@ -1639,35 +1639,41 @@ __global__ void k_xupdate_riccati(int N, int64_t batch, size_t ld, const double 
     for (int i = 0; i < 6; ++i) x[(size_t)(9 * N + i) * ld + p] = s[i];
 }
 
-// Retirement of the condensed TF32 path: for the finished working-set columns c = fin[t], x = exact FP64 Riccati
-// x-update (same arithmetic as k_xupdate_riccati) of rt = (z - u) - (inc_hi + inc_lo) on the split rows, zero elsewhere,
-// written to the home column orig[c].  d: scratch [3N][ld_d], one column per t.
-// REFRESH: the same solve for every working-set column (fin == nullptr, no increment subtracted: rt = z - u is the
-// right-hand side of the NEXT iteration), written to the split rows of the accumulated x_R (home = xacc, pitch
-// ld_home = ld_in) -- removes the rounding accumulated so far; the caller then zeroes the increment buffers.
-template <bool HAS_C, bool REFRESH>
+// Exact FP64 Riccati solves of the condensed TF32 path (same arithmetic as k_xupdate_riccati), one thread per problem.
+//   MODE 0 (retire, dense layout): for the finished working-set columns c = fin[t], rt = (z - u) - (inc_hi + inc_lo) on
+//          the split rows (the right-hand side the problem's last iteration used), x written to the home column orig[c].
+//   MODE 1 (refresh): for every running column, rt = z - u (the right-hand side of the NEXT iteration), x written to the
+//          split rows of the accumulated x_R (out = xacc, pitch ld_out); the caller then zeroes the increment buffers.
+//   MODE 2 (retire, Riccati layout): as MODE 0 but only the backward sweep; d is left in the working set (out = the
+//          travelling d array, column c) for k_output.
+// zu_compact: z / u rows are the compact split rows (Riccati layout) instead of the full rows.  d: scratch [3N][ld_d],
+// one column per t (MODE 0 / 1).
+template <bool HAS_C, int MODE>
 __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int *__restrict__ bdesc, const double *s0,
-                               const double *z, const double *u, const float *inc_hi, const float *inc_lo, size_t ld_in,
-                               const int *fin, int n_fin, const int *orig, double *d, size_t ld_d, double *home,
-                               size_t ld_home, const int *status)
+                               const double *z, const double *u, int zu_compact, const float *inc_hi, const float *inc_lo,
+                               size_t ld_in, const int *fin, int n_fin, const int *orig, double *d, size_t ld_d, double *out,
+                               size_t ld_out, const int *status)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_fin) return;
-    if (REFRESH && status[t] != ST_RUNNING) return;     // finished columns keep the x_R of their last iteration
-    const size_t c = REFRESH ? (size_t)t : (size_t)fin[t], h = REFRESH ? c : (orig ? (size_t)orig[c] : c);
-    auto put = [&](int row, double v) {
-        if (!REFRESH) { home[(size_t)row * ld_home + h] = v; return; }
-        const int bd = bdesc[row / 3];
-        if ((bd & 0xff) != BLK_NONE) home[(size_t)(3 * (bd >> 8) + row % 3) * ld_home + h] = v;
-    };
+    if (MODE == 1 && status[t] != ST_RUNNING) return;     // finished columns keep the x_R of their last iteration
+    const size_t c = MODE == 1 ? (size_t)t : (size_t)fin[t];
+    const size_t h = MODE == 0 ? (orig ? (size_t)orig[c] : c) : c;
+    const size_t dcol = MODE == 2 ? c : (size_t)t;
     FacRef<true> F;
     F.base = fac;
     F.ld = 0;
+    auto put = [&](int row, double v) {
+        if (MODE == 0) { out[(size_t)row * ld_out + h] = v; return; }
+        const int bd = bdesc[row / 3];
+        if ((bd & 0xff) != BLK_NONE) out[(size_t)(3 * (bd >> 8) + row % 3) * ld_out + h] = v;
+    };
     auto rt = [&](int row) -> double {
         const int bd = bdesc[row / 3];
         if ((bd & 0xff) == BLK_NONE) return 0.0;
-        const size_t o = (size_t)row * ld_in + c, oc = (size_t)(3 * (bd >> 8) + row % 3) * ld_in + c;
-        if (REFRESH) return z[o] - u[o];
+        const size_t oc = (size_t)(3 * (bd >> 8) + row % 3) * ld_in + c;
+        const size_t o = zu_compact ? oc : (size_t)row * ld_in + c;
+        if (MODE == 1) return z[o] - u[o];
         const double inc = (double)inc_hi[oc] + (inc_lo ? (double)inc_lo[oc] : 0.0);
         return (z[o] - u[o]) - inc;
     };
@@ -1691,7 +1697,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
             acc = fma(F(k, F_HINV + HINV_LD * j + 2), ra[2], acc);
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc = fma(F(k, F_E + 6 * j + i), g[i], acc);
-            d[(size_t)(3 * k + j) * ld_d + t] = acc;
+            d[(size_t)(3 * k + j) * ld_d + dcol] = acc;
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -1705,6 +1711,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
 #pragma unroll
         for (int i = 0; i < 6; ++i) g[i] = pn[i];
     }
+    if (MODE == 2) return;
     double s[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) s[i] = s0[(size_t)i * ld_in + c];
@@ -1712,7 +1719,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
         double a[3], sn[6];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            double acc = d[(size_t)(3 * k + j) * ld_d + t];
+            double acc = d[(size_t)(3 * k + j) * ld_d + dcol];
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc = fma(F(k, F_K + 6 * j + i), s[i], acc);
             a[j] = acc;
@@ -1873,7 +1880,7 @@ template <int CH, int MINW>   // MINW: resident warps per SM the register alloca
 __global__ void __launch_bounds__(32 * CH, MINW / CH)
 k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ bdesc, int64_t batch, size_t ld,
                  const double *par, int par_batched, double alpha, const float *__restrict__ dx32, double *xacc,
-                 double *z, double *u, float *rt_hi, float *rt_lo, const DenseStep ds)
+                 double *z, double *u, int zu_compact, float *rt_hi, float *rt_lo, const DenseStep ds)
 {
     __shared__ double red[CH][5][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -1891,7 +1898,7 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
             double xb[3], zo[3], uo[3], v[3], zn[3];
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
+                const size_t oc = (size_t)(3 * j + e) * ld + p, o = zu_compact ? oc : (size_t)(3 * b + e) * ld + p;
                 xb[e] = ld_stream(xacc + oc) + (double)__ldcs(dx32 + oc);
                 st_stream(xacc + oc, xb[e]);
                 zo[e] = ld_stream(z + o);
@@ -1908,7 +1915,7 @@ k_prox_cond_tf32(int nsb, const int *__restrict__ sblk, const int *__restrict__ 
             }
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                const size_t o = (size_t)(3 * b + e) * ld + p, oc = (size_t)(3 * j + e) * ld + p;
+                const size_t oc = (size_t)(3 * j + e) * ld + p, o = zu_compact ? oc : (size_t)(3 * b + e) * ld + p;
                 const double un = v[e] - zn[e];
                 const double dr = xb[e] - zn[e];
                 const double dz = zn[e] - zo[e];

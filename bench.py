@@ -195,10 +195,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--xupdate", default="riccati", choices=["riccati", "dense"],
-                    help="x-update of the solve (default: the bit-exact FP64 Riccati path)")
+    ap.add_argument("--xupdate", default="auto", choices=["auto", "riccati", "dense"],
+                    help="x-update of the solve (default auto = the bit-exact FP64 Riccati path unless --precision tf32)")
     ap.add_argument("--precision", default="f64", choices=["f64", "tf32"],
-                    help="tf32 (with --xupdate dense): the tcgen05 TF32x3 GEMM path, a stated 1e-4 precision class")
+                    help="tf32: tensor cores allowed (tcgen05 TF32x3 GEMM on the increment, FP64 accumulation). With "
+                         "--xupdate dense throughout; with auto only once the working set is narrow (DESIGN 6)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,8 +226,10 @@ def main():
     prob, opts = make_workload(pkg.problems, name, per_gpu, rank)
     if args.chunk:
         opts["chunk"] = args.chunk
-    if args.xupdate != "riccati" or args.precision != "f64":
-        opts["xupdate"], opts["precision"] = args.xupdate, args.precision
+    if args.xupdate != "auto":
+        opts["xupdate"] = args.xupdate
+    if args.precision == "tf32":
+        opts["precision"] = "tf32"
     N = int(prob["A"].shape[1])
     n = 9 * N + 6
     nsplit = nsplit_of(prob)
@@ -304,7 +307,16 @@ def main():
             traffic = json.load(open(tpath)).get(name)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_admm_iterate_pptma" if prob["A"].shape[0] > 1 else "k_admm_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_name = "k_admm_iterate_pptma" if prob["A"].shape[0] > 1 else "k_admm_iterate"
+    if args.xupdate == "dense" and args.precision == "tf32":
+        # condensed incremental tensor-core path: the timed launches are the GEMM + prox pair.  Per
+        # problem-iteration the prox kernel moves 60 B per split entry (x_R, z, u read+write, product read, increment
+        # hi/lo write) and the GEMM reads the increment (8 B) and writes the product (4 B) per split entry
+        alg_bytes_per_pi = 72.0 * nsplit
+        achieved = (iters_rank * alg_bytes_per_pi) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        kernel_name = "k_dense_xupdate_tf32 + k_prox_cond_tf32 (pair, one graph node each per iteration)"
+        traffic = None
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_problem_iteration": alg_bytes_per_pi,
                 "kernel_ms_per_step": kernel_ms / max(args.steps, 1),
@@ -377,7 +389,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if args.precision == "f64" else "tf32x3 x-update (fp32 accumulate), f64 prox/dual/residuals",
+                "dtype": "f64" if args.precision == "f64" else
+                ("tf32x3 x-update increments (f64 accumulation), f64 prox/dual/residuals" if args.xupdate == "dense" else
+                 "f64 Riccati kernel while wide, tf32x3 x-update increments (f64 accumulation) once narrow"),
                 "data": "synthetic",
                 "config": {"workload": WORKLOADS[name][3], "name": name, "xupdate": args.xupdate,
                            "problems_per_gpu": per_gpu,

@@ -65,7 +65,8 @@ enum { ADMMB_ST_CONVERGED = 0, ADMMB_ST_MAX_ITER = 1, ADMMB_ST_NAN = 2 };
 
 /* x-update selection (SURVEY 8(a) rows a2 / a2') and arithmetic */
 enum { ADMMB_XUPDATE_AUTO = 0, ADMMB_XUPDATE_DENSE = 1, ADMMB_XUPDATE_RICCATI = 2 };
-enum { ADMMB_PREC_FP64 = 0, ADMMB_PREC_TF32 = 1 };   /* TF32 applies to the dense x-update only */
+enum { ADMMB_PREC_FP64 = 0, ADMMB_PREC_TF32 = 1 };   /* TF32: tensor cores allowed -- with XUPDATE_DENSE throughout, with
+                                                        XUPDATE_AUTO once the working set is narrow; not with RICCATI */
 
 typedef struct admmb_ctx *admmb_handle;
 

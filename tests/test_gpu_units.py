@@ -173,7 +173,7 @@ def test_bad_arguments_are_refused_not_crashed(solver, pkg, P):
     prob, opts = P.cfg2_cw_batch(batch=4, N=5, seed=1)
     E = pkg._lib.E_BADARG
     for bad in (dict(rho=-1.0), dict(alpha=2.5), dict(max_iter=0), dict(adapt_rho=1, adapt_tau=1.0),
-                dict(precision="tf32"), dict(xupdate="dense", history=1)):
+                dict(precision="tf32", xupdate="riccati"), dict(xupdate="dense", history=1)):
         with pytest.raises(pkg.AdmmError) as e:
             solver.solve(prob, dict(opts, **bad))
         assert e.value.code == E
@@ -356,3 +356,53 @@ def test_tf32_incremental_reaches_1e8_where_absolute_form_stalls(solver, P):
     both = (ref["status"] == 0) & (inc["status"] == 0)
     ratio = inc["iters"][both].astype(float) / ref["iters"][both]
     assert 0.97 < np.median(ratio) < 1.03
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("switch", [700, 100000])
+def test_tf32_auto_riccati_then_tensor_core_tail(solver, cpu_oracle, P, switch):
+    """precision='tf32' with xupdate='auto': the FP64 Riccati kernel runs while the working set is wide, the condensed
+    incremental tensor-core pair takes over the compacted working set once it is narrow (switch=700: after ~half of
+    the 1,500 problems have finished; switch=100000: from iteration 0).  Problems that finish in the first phase are
+    bit-identical to the oracle; the others follow it within the TF32 class; every returned x satisfies the dynamics
+    to FP64 round-off (it is rebuilt from the backward-sweep result d by the Riccati path's output kernel)."""
+    import os
+    prob, opts = P.cfg2_cw_batch(batch=1500, N=20, seed=31)
+    opts = dict(opts, max_iter=6000, abstol=1e-6, reltol=1e-6)
+    xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
+    os.environ["ADMMB_TF32_SWITCH"] = str(switch)
+    try:
+        x, z, u, h = solver.solve(prob, dict(opts, precision="tf32"))
+    finally:
+        del os.environ["ADMMB_TF32_SWITCH"]
+    assert (hr["status"] == 0).mean() > 0.6
+    assert (h["status"] == hr["status"]).mean() > 0.99
+    both = (h["status"] == 0) & (hr["status"] == 0)
+    di = np.abs(h["iters"][both].astype(int) - hr["iters"][both].astype(int))
+    assert (di <= 0.02 * hr["iters"][both] + 2).mean() > 0.98
+    if switch == 700:
+        # the first finishers never saw the tensor cores: bit-identical
+        early = both & (hr["iters"] <= np.sort(hr["iters"][both])[200])
+        assert early.sum() >= 200
+        np.testing.assert_array_equal(h["iters"][early], hr["iters"][early])
+        np.testing.assert_array_equal(x[early], xr[early])
+        np.testing.assert_array_equal(z[early], zr[early])
+        np.testing.assert_array_equal(u[early], ur[early])
+    from oracle import admm_ocp as O
+    fz, fr = O.objective(prob, z)[both], O.objective(prob, zr)[both]
+    assert np.abs(fz - fr).max() <= 1e-4 * np.abs(fr).max()
+    sx = np.abs(xr).max()
+    assert np.abs(x[both] - xr[both]).max() <= 5e-3 * sx
+    A, B = np.asarray(prob["A"])[0], np.asarray(prob["B"])[0]
+    N = A.shape[0]
+    X = x[:, :9 * N].reshape(-1, N, 9)
+    s_, a_ = X[:, :, :6], X[:, :, 6:]
+    s_next = np.concatenate([s_[:, 1:], x[:, 9 * N:].reshape(-1, 1, 6)], axis=1)
+    res = s_next - np.einsum("kij,pkj->pki", A, s_) - np.einsum("kij,pkj->pki", B, a_)
+    assert np.abs(res).max() <= 1e-12 * sx
+    # the reported residual (from the accumulated x_R) matches the returned iterates (exact x - z on the split rows)
+    # up to the rounding x_R has accumulated since its last refresh
+    rows = np.repeat(np.asarray(prob["block_type"]) != P.BLK_NONE, 3)
+    r = np.linalg.norm((x - z)[:, rows], axis=1)
+    np.testing.assert_allclose(r[both], h["r_norm"][both], rtol=5e-2, atol=3e-8 * sx)
