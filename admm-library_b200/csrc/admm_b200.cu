@@ -686,6 +686,7 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
         if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
         if (has_P && (op->adapt_rho || pb->rho0)) return fail(h, ADMMB_E_BADARG, "dense x-update with P != 0 needs one shared rho");
         if (op->history) return fail(h, ADMMB_E_BADARG, "history is not recorded on the dense path");
+        if (op->adapt_rho) return fail(h, ADMMB_E_BADARG, "adaptive rho is not implemented on the dense path (use xupdate = auto / riccati)");
     }
     return ADMMB_OK;
 }

@@ -173,7 +173,8 @@ def test_bad_arguments_are_refused_not_crashed(solver, pkg, P):
     prob, opts = P.cfg2_cw_batch(batch=4, N=5, seed=1)
     E = pkg._lib.E_BADARG
     for bad in (dict(rho=-1.0), dict(alpha=2.5), dict(max_iter=0), dict(adapt_rho=1, adapt_tau=1.0),
-                dict(precision="tf32", xupdate="riccati"), dict(xupdate="dense", history=1)):
+                dict(precision="tf32", xupdate="riccati"), dict(xupdate="dense", history=1),
+                dict(xupdate="dense", adapt_rho=1)):
         with pytest.raises(pkg.AdmmError) as e:
             solver.solve(prob, dict(opts, **bad))
         assert e.value.code == E
@@ -406,3 +407,52 @@ def test_tf32_auto_riccati_then_tensor_core_tail(solver, cpu_oracle, P, switch):
     rows = np.repeat(np.asarray(prob["block_type"]) != P.BLK_NONE, 3)
     r = np.linalg.norm((x - z)[:, rows], axis=1)
     np.testing.assert_allclose(r[both], h["r_norm"][both], rtol=5e-2, atol=3e-8 * sx)
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["affine", "single_pass", "batched_par"])
+def test_tf32_condensed_variants(solver, cpu_oracle, P, variant):
+    """Less-travelled branches of the condensed tensor-core path: affine dynamics (c != 0: k_tf32_final_x<true, ...> and
+    the x_R initialisation carry the offset, the increments do not), single-pass TF32 operands (ADMMB_TF32_SINGLE: no
+    lo buffers), per-problem prox parameters (the parameter array travels with the working set)."""
+    import os
+    prob, opts = P.cfg2_cw_batch(batch=200, N=20, seed=41)
+    opts = dict(opts, max_iter=5000, abstol=1e-5, reltol=1e-5)
+    prob = dict(prob)
+    if variant == "affine":
+        rng = np.random.default_rng(3)
+        prob["c"] = 1e-3 * rng.standard_normal((1, 20, 6))
+    if variant == "batched_par":
+        rng = np.random.default_rng(4)
+        bp = np.repeat(np.asarray(prob["block_par"]), 200, axis=0)
+        bp[:, :, P.PAR_LAM] *= rng.uniform(0.5, 2.0, size=(200, 1))
+        prob["block_par"] = bp
+    xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
+    if variant == "single_pass":
+        os.environ["ADMMB_TF32_SINGLE"] = "1"
+    try:
+        x, z, u, h = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32", chunk=20))
+    finally:
+        os.environ.pop("ADMMB_TF32_SINGLE", None)
+    assert (hr["status"] == 0).mean() > 0.5
+    # (single-pass operands perturb every increment by ~7e-4 of the step: slow problems near max_iter may flip)
+    assert (h["status"] == hr["status"]).mean() > (0.85 if variant == "single_pass" else 0.97)
+    both = (h["status"] == 0) & (hr["status"] == 0)
+    ratio = h["iters"][both].astype(float) / hr["iters"][both]
+    assert 0.9 < np.median(ratio) < 1.1
+    from oracle import admm_ocp as O
+    fz, fr = O.objective(prob, z)[both], O.objective(prob, zr)[both]
+    assert np.abs(fz - fr).max() <= (1e-2 if variant == "single_pass" else 1e-3) * np.abs(fr).max()
+    sx = np.abs(xr).max()
+    assert np.abs(x[both] - xr[both]).max() <= 2e-2 * sx
+    # dynamics of the returned x, incl. the affine term
+    A, B = np.asarray(prob["A"])[0], np.asarray(prob["B"])[0]
+    N = A.shape[0]
+    X = x[:, :9 * N].reshape(-1, N, 9)
+    s_, a_ = X[:, :, :6], X[:, :, 6:]
+    s_next = np.concatenate([s_[:, 1:], x[:, 9 * N:].reshape(-1, 1, 6)], axis=1)
+    res = s_next - np.einsum("kij,pkj->pki", A, s_) - np.einsum("kij,pkj->pki", B, a_)
+    if prob.get("c") is not None:
+        res = res - np.asarray(prob["c"])[0][None]
+    assert np.abs(res).max() <= 1e-12 * sx
