@@ -109,7 +109,7 @@ struct Shard {
         DevBuf<unsigned char> work[2];
     };
     ColArray cols[C_COUNT];
-    DevBuf<int> orig[2], keep_list, fin_list, split_counts;
+    DevBuf<int> orig[2], keep_list, fin_list, split_counts, snap;
     int cur_set = -1;
     int64_t width = 0;
     size_t ld_cur = 0;
@@ -127,6 +127,7 @@ struct Shard {
         cols[c].cur_override = nullptr;
     }
     void repack(int n_keep, int n_fin);
+    bool pad_warps = getenv("ADMMB_NO_PAD") == nullptr;
     DevBuf<unsigned long long> counters;   // [0] refactor count, [1] converged, [2] sum iters, [3] max iters
     DenseState dense;
 
@@ -290,6 +291,7 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     fac_status.alloc(ld);
     keep_list.alloc(ld);
     fin_list.alloc(ld);
+    snap.alloc(ld);
     split_counts.alloc(2);
     counters.alloc(4);
     CK(cudaMemsetAsync(fac_status.p, 0, sizeof(int) * ld, stream));
@@ -321,16 +323,17 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
 // ones into a dense, 32-aligned prefix of the other ping-pong buffer
 void Shard::repack(int n_keep, int n_fin)
 {
-    const unsigned gf = (unsigned)((n_fin + 127) / 128), gk = (unsigned)((n_keep + 127) / 128);
+    const unsigned gf = (unsigned)((n_fin + 127) / 128);
     auto rows_grid = [](int rows) { return (unsigned)std::min(rows, 64); };
     if (cur_set >= 0 && n_fin > 0) {
         for (int c = 0; c < C_COUNT; ++c) {
             ColArray &a = cols[c];
             if (a.rows == 0 || !a.retire) continue;
             dim3 grid(gf, rows_grid(a.rows));
+            const int *skip = (c == C_Z || c == C_U || c == C_D) ? snap.p : nullptr;
             if (a.elem == 8)
                 k_scatter_cols<double><<<grid, 128, 0, stream>>>((const double *)a.work[cur_set].p, ld_cur, a.rows,
-                                                                 fin_list.p, n_fin, orig[cur_set].p, (double *)a.home, ld);
+                                                                 fin_list.p, n_fin, orig[cur_set].p, (double *)a.home, ld, skip);
             else
                 k_scatter_cols<int><<<grid, 128, 0, stream>>>((const int *)a.work[cur_set].p, ld_cur, a.rows, fin_list.p,
                                                               n_fin, orig[cur_set].p, (int *)a.home, ld);
@@ -338,11 +341,23 @@ void Shard::repack(int n_keep, int n_fin)
         }
         CK(cudaGetLastError());
     }
+    CK(cudaMemsetAsync(snap.p, 0, sizeof(int) * ld, stream));   // the next working set starts without snapshots
     if (n_keep == 0) { width = 0; return; }
+    // Pad the working set to whole warps with COPIES of its last running problem (own columns, same home column):
+    // a launch in which one warp has idle lanes runs ~25 % slower on a narrow working set (measured: 8,160 problems
+    // 1.62 ms per 50 iterations, 8,161 or 8,191 problems 2.02-2.04 ms).  The copies evolve identically to their
+    // source and retire to the same home column with the same values.
+    if (pad_warps && (n_keep & 31)) {
+        const int n_pad = (int)round_up((size_t)n_keep, 32);
+        k_pad_list<<<1, 32, 0, stream>>>(keep_list.p, n_keep, n_pad);
+        ++launches;
+        n_keep = n_pad;
+    }
+    const unsigned gk2 = (unsigned)((n_keep + 127) / 128);
     const int nxt = cur_set == 0 ? 1 : 0;
     const size_t ld_new = round_up((size_t)n_keep, 32);
     orig[nxt].alloc(ld_new);
-    k_compose_orig<<<gk, 128, 0, stream>>>(cur_set < 0 ? nullptr : orig[cur_set].p, keep_list.p, n_keep, orig[nxt].p);
+    k_compose_orig<<<gk2, 128, 0, stream>>>(cur_set < 0 ? nullptr : orig[cur_set].p, keep_list.p, n_keep, orig[nxt].p);
     ++launches;
     for (int c = 0; c < C_COUNT; ++c) {
         ColArray &a = cols[c];
@@ -350,7 +365,7 @@ void Shard::repack(int n_keep, int n_fin)
         a.work[nxt].alloc((size_t)a.rows * ld_new * a.elem);
         const void *src = a.cur_override ? a.cur_override : (cur_set < 0 ? a.home : (const void *)a.work[cur_set].p);
         a.cur_override = nullptr;
-        dim3 grid(gk, rows_grid(a.rows));
+        dim3 grid(gk2, rows_grid(a.rows));
         if (a.elem == 8)
             k_gather_cols<double><<<grid, 128, 0, stream>>>((const double *)src, ld_cur, a.rows, keep_list.p, n_keep,
                                                             (double *)a.work[nxt].p, ld_new);
@@ -479,19 +494,24 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         width = batch;
         ld_cur = ld;
         const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
+        const bool zombies_enabled = getenv("ADMMB_NO_ZOMBIES") == nullptr;
+        CK(cudaMemsetAsync(snap.p, 0, sizeof(int) * ld, stream));
 
         // launches get longer once few problems finish per launch: the host round trip (split, count
         // read-back, repack) then costs relatively less and nothing is lost in early-exit granularity
         const int chunk_max = op->chunk > 0 ? op->chunk : 400;
-        // below this many running problems one warp's serial sweep bounds the Riccati kernel (~42 us per iteration)
-        // and the GEMM + prox pair is faster
-        const int64_t tail_width = getenv("ADMMB_TF32_SWITCH") ? atoll(getenv("ADMMB_TF32_SWITCH")) : 12288;
+        // below this many running problems one warp's serial sweep bounds the Riccati kernel (~33 us per iteration)
+        // and the GEMM + prox pair is faster (32 us at 8,192, 21 us at 1,024: DESIGN 6.3)
+        const int64_t tail_width = getenv("ADMMB_TF32_SWITCH") ? atoll(getenv("ADMMB_TF32_SWITCH")) : 8192;
         int done_iters = 0;
         while (width > 0 && done_iters < op->max_iter && !(tf32_tail && width <= tail_width)) {
             P.chunk = chunk;
             P.ld = ld_cur;
             P.n_active = (int)width;
             P.orig = cur_set < 0 ? nullptr : orig[cur_set].p;
+            const bool zomb = cur_set >= 0 && zombies_enabled;
+            P.z_home = zomb ? z.p : nullptr; P.u_home = zomb ? u.p : nullptr; P.d_home = zomb ? d.p : nullptr;
+            P.home_ld = ld; P.rows_zu = rows_zu; P.snap = snap.p;
             P.fac = shared_factor ? fac.p : colptr<double>(C_FAC);
             P.fac_rw = colptr<double>(C_FAC);
             P.fac_dec = (shared_factor || !decoupled) ? fac_dec.p : colptr<double>(C_FACDEC);

@@ -318,6 +318,12 @@ struct IterParams {
     double *hist;                 // 5 x [max_iter][ld] or nullptr
     size_t hist_stride;
     unsigned long long *refac_count;
+    // finished lanes keep iterating until the launch ends (see k_admm_iterate): at the moment a problem finishes its
+    // z, u, d columns are copied to their home columns and snap[p] is set so that the repack does not retire them again
+    double *z_home, *u_home, *d_home;   // nullptr: working set == home arrays (finished lanes leave the loop instead)
+    size_t home_ld;
+    int rows_zu;
+    int *snap;
     double alpha, oma, reltol, sqrtn_abs, mu, tau, inv_tau;
     int adapt, every, until, max_iter, chunk, has_P;
 };
@@ -1293,9 +1299,10 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     mbar_wait(mbar, 0);
 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n_active) return;
+    const bool live = t < P.n_active && P.status[t] == ST_RUNNING;
+    const unsigned wmask = __ballot_sync(0xffffffffu, live);   // the lanes of this warp that run the loop
+    if (!live) return;
     const size_t p = (size_t)t;       // column of the (densely repacked) working set: always aligned
-    if (P.status[p] != ST_RUNNING) return;
 
     FacRef<FSH> F;
     F.base = FSH ? (FSMEM ? facS : fac_src) : fac_src + p;
@@ -1307,47 +1314,75 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     int it = P.iters[p];
     int st = ST_RUNNING;
     double r_norm = 0.0, s_norm = 0.0, eps_pri = 0.0, eps_dual = 0.0;
-    for (int cnt = 0; cnt < P.chunk && st == ST_RUNNING; ++cnt) {
-        ++it;
+    // A warp in which some lane has left the loop runs the remaining iterations ~25 % slower (its stores no longer
+    // cover whole 32-byte sectors, so its own reloads wait for sector fills; measured: 1.62 ms per 50 iterations with
+    // full warps, 2.02-2.09 ms as soon as one lane of one warp is idle) -- and on a narrow working set the slowest
+    // warp is the launch time.  So a lane whose problem finishes does not leave: it copies its final z, u, d to the
+    // home columns (snapshot), then keeps iterating on its working column (whose contents no longer matter) until
+    // every lane of the warp is done or the launch ends.  Needs a working set that is a copy (P.z_home != nullptr).
+    const bool zombies = P.z_home != nullptr;
+    bool done = false;
+    double sigma_fin = 1.0;
+    for (int cnt = 0; cnt < P.chunk; ++cnt) {
+        if (!done) ++it;
         double nr[5];
         if (MODE == 2) admm_iteration_dec<FSH, FSMEM, HAS_C, HAS_Q, ADAPT, (LOWOCC ? 4 : 2)>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else if (MODE == 1) admm_iteration_fast<FSH, FSMEM, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, par_sbase, rho, sigma, nr);
         else admm_iteration<FSH, HAS_C, HAS_Q, ADAPT>(P, p, F, bdS, parS, rho, sigma, nr);
         sigma = 1.0;
-        r_norm = sqrt(nr[0]);
-        s_norm = rho * sqrt(nr[1]);
-        const double nx = sqrt(nr[2]), nz = sqrt(nr[3]);
-        eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
-        eps_dual = fma(P.reltol, rho * sqrt(nr[4]), P.sqrtn_abs);
-        if (P.hist) {
-            const size_t h = (size_t)(it - 1) * P.hist_ld + (P.orig ? (size_t)P.orig[p] : p);   // home column
-            P.hist[h] = r_norm;
-            P.hist[h + P.hist_stride] = s_norm;
-            P.hist[h + 2 * P.hist_stride] = eps_pri;
-            P.hist[h + 3 * P.hist_stride] = eps_dual;
-            P.hist[h + 4 * P.hist_stride] = rho;
-        }
-        if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; break; }
-        if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; break; }
-        if (ADAPT && (it % P.every) == 0 && it < P.max_iter && (P.until <= 0 || it <= P.until)) {
-            bool ch = false;
-            if (r_norm > P.mu * s_norm) {
-                if (!(rho * P.tau > RHO_MAX)) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
-            } else if (s_norm > P.mu * r_norm) {
-                if (!(rho * P.inv_tau < RHO_MIN)) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+        if (!done) {
+            r_norm = sqrt(nr[0]);
+            s_norm = rho * sqrt(nr[1]);
+            const double nx = sqrt(nr[2]), nz = sqrt(nr[3]);
+            eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
+            eps_dual = fma(P.reltol, rho * sqrt(nr[4]), P.sqrtn_abs);
+            if (P.hist) {
+                const size_t h = (size_t)(it - 1) * P.hist_ld + (P.orig ? (size_t)P.orig[p] : p);   // home column
+                P.hist[h] = r_norm;
+                P.hist[h + P.hist_stride] = s_norm;
+                P.hist[h + 2 * P.hist_stride] = eps_pri;
+                P.hist[h + 3 * P.hist_stride] = eps_dual;
+                P.hist[h + 4 * P.hist_stride] = rho;
             }
-            if (ch && !FSH && P.has_P) {
-                const size_t off = P.raw_batched ? p : 0, ldr = P.raw_batched ? P.ld : 1;
-                int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
-                                             P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
-                                             ldr, rho, bdS, P.fac_rw + p, P.ld);
-                atomicAdd(P.refac_count, 1ULL);
-                if (bad) { st = ST_NAN; break; }
-                if (MODE == 2) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
+            if (!(isfinite(r_norm) && isfinite(s_norm))) st = ST_NAN;
+            else if (r_norm < eps_pri && s_norm < eps_dual) st = ST_CONVERGED;
+            else {
+                if (ADAPT && (it % P.every) == 0 && it < P.max_iter && (P.until <= 0 || it <= P.until)) {
+                    bool ch = false;
+                    if (r_norm > P.mu * s_norm) {
+                        if (!(rho * P.tau > RHO_MAX)) { rho = rho * P.tau; sigma = P.inv_tau; ch = true; }
+                    } else if (s_norm > P.mu * r_norm) {
+                        if (!(rho * P.inv_tau < RHO_MIN)) { rho = rho * P.inv_tau; sigma = P.tau; ch = true; }
+                    }
+                    if (ch && !FSH && P.has_P) {
+                        const size_t off = P.raw_batched ? p : 0, ldr = P.raw_batched ? P.ld : 1;
+                        int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
+                                                     P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
+                                                     ldr, rho, bdS, P.fac_rw + p, P.ld);
+                        atomicAdd(P.refac_count, 1ULL);
+                        if (bad) st = ST_NAN;
+                        else if (MODE == 2) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
+                    }
+                }
+                if (st == ST_RUNNING && it >= P.max_iter) st = ST_MAX_ITER;
+            }
+            if (st != ST_RUNNING) {
+                done = true;
+                sigma_fin = sigma;
+                if (!zombies) break;
+                const size_t h = (size_t)P.orig[p];
+                for (int r = 0; r < P.rows_zu; ++r) {
+                    P.z_home[(size_t)r * P.home_ld + h] = P.z[(size_t)r * P.ld + p];
+                    P.u_home[(size_t)r * P.home_ld + h] = P.u[(size_t)r * P.ld + p];
+                }
+                for (int r = 0; r < 3 * P.N; ++r) P.d_home[(size_t)r * P.home_ld + h] = P.d[(size_t)r * P.ld + p];
+                P.snap[p] = 1;
+                sigma = 1.0;
             }
         }
-        if (it >= P.max_iter) { st = ST_MAX_ITER; break; }
+        if (zombies && __all_sync(wmask, done)) break;
     }
+    if (done) sigma = sigma_fin;
     P.iters[p] = it;
     P.rho[p] = rho;
     if (ADAPT) P.usc[p] = sigma;
@@ -1404,11 +1439,12 @@ __global__ void k_gather_cols(const T *in, size_t ld_in, int rows, const int *sr
 // home[r][orig[c]] = in[r][c] for the finished columns c = fin[t]
 template <typename T>
 __global__ void k_scatter_cols(const T *in, size_t ld_in, int rows, const int *fin, int n, const int *orig, T *home,
-                               size_t ld_home)
+                               size_t ld_home, const int *skip = nullptr)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const size_t c = (size_t)fin[t], h = (size_t)orig[c];
+    if (skip && skip[c]) return;      // already copied home by the kernel at the moment the problem finished
     for (int r = blockIdx.y; r < rows; r += gridDim.y) home[(size_t)r * ld_home + h] = in[(size_t)r * ld_in + c];
 }
 
@@ -1421,6 +1457,13 @@ __global__ void k_compose_orig(const int *orig_old, const int *src, int n, int *
 
 __global__ void k_add_int(int *a, int v) { *a += v; }
 __global__ void k_set_int(int *a, int v) { *a = v; }
+
+// keep[n .. n_pad) = keep[n-1]: the working set is padded to whole warps with copies of a running problem
+__global__ void k_pad_list(int *keep, int n, int n_pad)
+{
+    const int t = n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_pad) keep[t] = keep[n - 1];
+}
 
 __global__ void k_iota(int *a, int n)
 {
