@@ -146,12 +146,28 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
     double sigma = ADAPT ? P.usc[p] : 1.0;
     int it = P.iters[p];
     double r_norm = 0.0, s_norm = 0.0, eps_pri = 0.0, eps_dual = 0.0;
+    // Lanes whose problem finishes in this launch keep iterating AND storing on their working column after copying
+    // the final z, u, d to the home columns (kernels.cuh, k_admm_iterate: keeps the warp's stores sector-complete);
+    // only when the working set is a copy (P.z_home != nullptr).
+    const bool zombies = P.z_home != nullptr;
+    bool zomb = false;
+    auto finished = [&]() {
+        if (!zombies) return;
+        const size_t h = (size_t)P.orig[p];
+        for (int r = 0; r < P.rows_zu; ++r) {
+            P.z_home[(size_t)r * P.home_ld + h] = P.z[(size_t)r * P.ld + p];
+            P.u_home[(size_t)r * P.home_ld + h] = P.u[(size_t)r * P.ld + p];
+        }
+        for (int r = 0; r < 3 * P.N; ++r) P.d_home[(size_t)r * P.home_ld + h] = P.d[(size_t)r * P.ld + p];
+        P.snap[p] = 1;
+        zomb = true;
+    };
     for (int cnt = 0; cnt < P.chunk; ++cnt) {
-        const bool act = st == ST_RUNNING;
-        if (!__any_sync(0xffffffffu, act)) break;
+        const bool run = st == ST_RUNNING;
+        if (!__any_sync(0xffffffffu, run)) break;
         double nr[5];
-        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C>>(P, p, F, bdS, par_sbase, rho, sigma, nr, stg, act);
-        if (!act) continue;
+        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
+        if (!run) continue;
         ++it;
         sigma = 1.0;
         r_norm = sqrt(nr[0]);
@@ -167,8 +183,8 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
             P.hist[h + 3 * P.hist_stride] = eps_dual;
             P.hist[h + 4 * P.hist_stride] = rho;
         }
-        if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; continue; }
-        if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; continue; }
+        if (!(isfinite(r_norm) && isfinite(s_norm))) { st = ST_NAN; finished(); continue; }
+        if (r_norm < eps_pri && s_norm < eps_dual) { st = ST_CONVERGED; finished(); continue; }
         if (ADAPT && (it % P.every) == 0 && it < P.max_iter && (P.until <= 0 || it <= P.until)) {
             bool ch = false;
             if (r_norm > P.mu * s_norm) {
@@ -182,13 +198,13 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
                                              P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
                                              ldr, rho, bdS, P.fac_rw + p, P.ld);
                 atomicAdd(P.refac_count, 1ULL);
-                if (bad) { st = ST_NAN; continue; }
+                if (bad) { st = ST_NAN; finished(); continue; }
                 pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
                 __threadfence();                                   // the next iteration's TMA reads must see the new record
                 asm volatile("fence.proxy.async.global;" ::: "memory");
             }
         }
-        if (it >= P.max_iter) st = ST_MAX_ITER;
+        if (it >= P.max_iter) { st = ST_MAX_ITER; finished(); }
     }
     if (was_running) {
         P.iters[p] = it;
