@@ -1314,10 +1314,10 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
     int it = P.iters[p];
     int st = ST_RUNNING;
     double r_norm = 0.0, s_norm = 0.0, eps_pri = 0.0, eps_dual = 0.0;
-    // A warp in which some lane has left the loop runs the remaining iterations ~25 % slower (its stores no longer
-    // cover whole 32-byte sectors, so its own reloads wait for sector fills; measured: 1.62 ms per 50 iterations with
-    // full warps, 2.02-2.09 ms as soon as one lane of one warp is idle) -- and on a narrow working set the slowest
-    // warp is the launch time.  So a lane whose problem finishes does not leave: it copies its final z, u, d to the
+    // A warp in which some lane has left the loop runs the remaining iterations ~25 % slower (measured: 1.62 ms per 50
+    // iterations with full warps, 2.02-2.09 ms as soon as one lane of one warp is idle; presumably because its stores
+    // no longer cover whole 32-byte sectors -- DESIGN 4.1c) -- and on a narrow working set the slowest warp is the
+    // launch time.  So a lane whose problem finishes does not leave: it copies its final z, u, d to the
     // home columns (snapshot), then keeps iterating on its working column (whose contents no longer matter) until
     // every lane of the warp is done or the launch ends.  Needs a working set that is a copy (P.z_home != nullptr).
     const bool zombies = P.z_home != nullptr;
