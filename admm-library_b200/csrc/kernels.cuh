@@ -1754,7 +1754,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
 #pragma unroll
         for (int i = 0; i < 6; ++i) g[i] = pn[i];
     }
-    if (MODE == 2) return;
+    if constexpr (MODE != 2) {   // MODE 2 keeps d only (k_output runs the forward sweep at download)
     double s[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) s[i] = s0[(size_t)i * ld_in + c];
@@ -1786,6 +1786,7 @@ __global__ void k_tf32_final_x(int N, const double *__restrict__ fac, const int 
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) put(9 * N + i, s[i]);
+    }
 }
 
 // Rows a3 + a4 alone (the streaming prox / dual / residual kernel, "C4"): reads x, z, u once,
