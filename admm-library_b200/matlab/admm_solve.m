@@ -14,6 +14,10 @@ function [x, z, u, hist] = admm_solve(prob, opts)
 %   prob.z0, prob.u0 [n x Bsz], prob.rho0 [Bsz]                                    (optional warm start)
 %   opts: rho alpha abstol reltol max_iter adapt_rho adapt_mu adapt_tau adapt_every adapt_until
 %         xupdate ('auto'|'dense'|'riccati') precision ('fp64'|'tf32') history gpus chunk
+%         precision 'fp64' (default): results bit-identical to the oracle admm_ocp.m order of operations.
+%         precision 'tf32': the tensor cores may be used (x-update increments as TF32x3 GEMMs, FP64 accumulation) --
+%         with xupdate 'dense' throughout, with 'auto' once few problems are still running; results then follow the
+%         FP64 iteration within a tolerance (same converged set down to 1e-8, iterates not bit-identical).
 %
 %   x, z, u  [n x Bsz],  n = 9N+6, stage-interleaved (s_0,a_0,...,s_N)
 %   hist.iters, hist.status (0 converged, 1 max_iter, 2 nan) [Bsz]; hist.r_norm, s_norm, eps_pri,

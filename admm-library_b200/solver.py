@@ -13,7 +13,9 @@ import numpy as np
 from . import _lib as L
 
 XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
-PRECISION = {"fp64": 0, "tf32": 1, "tf32_single": 2}   # tf32 = 3xTF32 split; tf32_single: unit entry point only
+# tf32: tensor cores allowed (3xTF32 split GEMM on the x-update increments; with xupdate="dense" throughout, with
+# "auto" once the working set is narrow); tf32_single: unit entry point only
+PRECISION = {"fp64": 0, "tf32": 1, "tf32_single": 2}
 FS = 156  # doubles per stage in a factor record (csrc/common.cuh)
 # name -> (offset, rows, cols, row stride) inside one record
 FAC_LAYOUT = dict(K=(0, 3, 6, 6), Acl=(18, 6, 6, 6), Hinv=(54, 3, 3, 4), E=(66, 3, 6, 6), A=(84, 6, 6, 6),
