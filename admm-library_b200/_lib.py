@@ -32,7 +32,8 @@ class Opts(C.Structure):
     _fields_ = [("rho", C.c_double), ("alpha", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
                 ("max_iter", C.c_int32), ("adapt_rho", C.c_int32), ("adapt_mu", C.c_double),
                 ("adapt_tau", C.c_double), ("adapt_every", C.c_int32), ("adapt_until", C.c_int32),
-                ("xupdate", C.c_int32), ("precision", C.c_int32), ("history", C.c_int32), ("chunk", C.c_int32)]
+                ("xupdate", C.c_int32), ("precision", C.c_int32), ("history", C.c_int32), ("chunk", C.c_int32),
+                ("kernel", C.c_int32), ("tf32_switch", C.c_int32), ("tf32_refresh", C.c_int32)]
 
 
 class Result(C.Structure):

@@ -88,6 +88,8 @@ struct Shard {
     bool tf32_tail = false;           // precision = tf32 with xupdate = auto: Riccati kernel while the working set is wide,
                                       // condensed incremental tensor-core pair once it is narrow (dense_tail)
     bool fast_pattern = false;   // stage states unsplit, every control split: prefetching kernel variant
+    int kernel_variant = KV_AUTO;  // opts.kernel of the current run (ADMMB_KERNEL_*)
+    int last_kernel = KV_THREAD;   // what the last launch ran
     bool decoupled = false;      // in-plane / cross-track structure proven on the factor: packed records
     int max_iter_alloc = 0;
     bool hist_alloc = false;
@@ -312,8 +314,16 @@ template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
     static const bool p2_default = getenv("ADMMB_P2") ? atoi(getenv("ADMMB_P2")) != 0 : true;
-    IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default};
-    if (FSH && FSMEM) launch_iterate_smem(c, P, adapt);
+    // widest working set the resident-tile kernel takes when the choice is the library's (tuning knob; no effect on results)
+    static const int64_t tile_width = getenv("ADMMB_TILE_WIDTH") ? atoll(getenv("ADMMB_TILE_WIDTH")) : 16384;
+    IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default, kernel_variant,
+                    rows_zu, device};
+    last_kernel = KV_THREAD;
+    if (FSH && FSMEM) {
+        const bool tile = kernel_variant == KV_TILE || (kernel_variant == KV_AUTO && P.n_active <= tile_width);
+        if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
+        else launch_iterate_smem(c, P, adapt);
+    }
     else if (FSH) launch_iterate_gshared(c, P, adapt);
     else if (!launch_iterate_pptma(c, P, adapt)) launch_iterate_pp(c, P, adapt);
     ++launches;
@@ -404,6 +414,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     CK(cudaSetDevice(device));
     const bool has_P = has_Q || has_R;
     const bool adapt = op->adapt_rho != 0;
+    kernel_variant = op->kernel;
     const unsigned gb = (unsigned)((batch + 127) / 128);
     CK(cudaEventRecord(ev0, stream));
     CK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 4, stream));
@@ -697,6 +708,7 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
         return fail(h, ADMMB_E_BADARG, "adaptive rho needs mu > 1, tau > 1, every >= 1");
     if (op->xupdate < 0 || op->xupdate > 2) return fail(h, ADMMB_E_BADARG, "xupdate must be an ADMMB_XUPDATE_* code");
     if (op->precision != ADMMB_PREC_FP64 && op->precision != ADMMB_PREC_TF32) return fail(h, ADMMB_E_BADARG, "bad precision");
+    if (op->kernel < ADMMB_KERNEL_AUTO || op->kernel > ADMMB_KERNEL_WG) return fail(h, ADMMB_E_BADARG, "kernel must be an ADMMB_KERNEL_* code");
     // TF32 + dense: the tensor-core path throughout; TF32 + auto: tensor cores are allowed where they are faster
     // (narrow working sets, eligible problems; otherwise the FP64 Riccati kernel runs)
     if (op->precision == ADMMB_PREC_TF32 && op->xupdate == ADMMB_XUPDATE_RICCATI)

@@ -19,11 +19,12 @@ struct OccTable {
     const void *kern = nullptr;
     size_t smem = 0;
     int num_sms = 0;
+    int device = -1;              // cudaFuncSetAttribute and the occupancy query are per device
     long cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 template <class K>
-static const OccTable &occ_table(K kern, size_t smem, int num_sms)
+static const OccTable &occ_table(K kern, size_t smem, int num_sms, int device)
 {
     static thread_local OccTable cache[32];
     static thread_local int used = 0;
@@ -31,7 +32,7 @@ static const OccTable &occ_table(K kern, size_t smem, int num_sms)
     size_t attr = 0;
     const OccTable *hit = nullptr;
     for (int i = 0; i < used; ++i)
-        if (cache[i].kern == (const void *)kern) {
+        if (cache[i].kern == (const void *)kern && cache[i].device == device) {
             attr = attr > cache[i].smem ? attr : cache[i].smem;
             if (cache[i].smem == smem && cache[i].num_sms == num_sms) hit = &cache[i];
         }
@@ -39,7 +40,7 @@ static const OccTable &occ_table(K kern, size_t smem, int num_sms)
     if (smem > attr) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (used == 32) used = 0;   // tiny cache: start over (re-queries, never wrong: attr is re-derived from live entries)
     OccTable &t = cache[used++];
-    t.kern = (const void *)kern; t.smem = smem; t.num_sms = num_sms;
+    t.kern = (const void *)kern; t.smem = smem; t.num_sms = num_sms; t.device = device;
     for (int i = 0; i < 8; ++i) {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (i + 1), smem) != cudaSuccess) occ = 0;
@@ -67,11 +68,13 @@ static void launch_iterate_kernel(const IterLaunchCtx &c, K1 kern, K2 kern_lowoc
 {
     // the uncapped-register build when it still holds the whole active set in one wave
     bool one_wave = false;
-    const int T_lo = pick_block(occ_table(kern_lowocc, smem, c.num_sms), P.n_active, &one_wave);
+    const int T_lo = pick_block(occ_table(kern_lowocc, smem, c.num_sms, c.device), P.n_active, &one_wave);
+    if (c.kernel == KV_THREAD) one_wave = false;            // pinned: the register-capped build
+    if (c.kernel == KV_THREAD_WIDE) one_wave = true;        // pinned: the uncapped build, however many waves
     if (one_wave) {
         kern_lowocc<<<(P.n_active + T_lo - 1) / T_lo, T_lo, smem, c.stream>>>(P);
     } else {
-        const int T = pick_block(occ_table(kern, smem, c.num_sms), P.n_active, &one_wave);
+        const int T = pick_block(occ_table(kern, smem, c.num_sms, c.device), P.n_active, &one_wave);
         kern<<<(P.n_active + T - 1) / T, T, smem, c.stream>>>(P);
     }
     CK(cudaGetLastError());
@@ -87,17 +90,19 @@ static void launch_iterate_tu(const IterLaunchCtx &c, const IterParams &P, bool 
     // Two problems per thread (iterate2.cuh): +8 % at full width (half the LDS traffic per problem), but a lone
     // warp gains nothing from the second stream (57 us vs 32 us per iteration for twice the work), so it is used
     // only when the working set is too wide for the uncapped one-problem build to hold it in one wave.
-    if (FSH && FSMEM && c.two_per_thread && c.fast_pattern && c.decoupled && !c.has_c && !c.has_q && !c.par_batched) {
+    if (FSH && FSMEM && (c.kernel == KV_AUTO || c.kernel == KV_THREAD2) && c.two_per_thread && c.fast_pattern && c.decoupled &&
+        !c.has_c && !c.has_q && !c.par_batched) {
         bool lo_fits = false, one_wave = false;
-        if (adapt) pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, true, 2, true>, smem, c.num_sms), P.n_active, &lo_fits);
-        else pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, false, 2, true>, smem, c.num_sms), P.n_active, &lo_fits);
+        if (adapt) pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, true, 2, true>, smem, c.num_sms, c.device), P.n_active, &lo_fits);
+        else pick_block(occ_table(k_admm_iterate<FSH, FSMEM, false, false, false, 2, true>, smem, c.num_sms, c.device), P.n_active, &lo_fits);
+        if (c.kernel == KV_THREAD2) lo_fits = false;        // pinned
         if (!lo_fits) {
             const int half = (P.n_active + 1) / 2;
             if (adapt) {
-                const int T = pick_block(occ_table(k_admm_iterate2<true>, smem, c.num_sms), half, &one_wave);
+                const int T = pick_block(occ_table(k_admm_iterate2<true>, smem, c.num_sms, c.device), half, &one_wave);
                 k_admm_iterate2<true><<<(P.n_active + 2 * T - 1) / (2 * T), T, smem, c.stream>>>(P);
             } else {
-                const int T = pick_block(occ_table(k_admm_iterate2<false>, smem, c.num_sms), half, &one_wave);
+                const int T = pick_block(occ_table(k_admm_iterate2<false>, smem, c.num_sms, c.device), half, &one_wave);
                 k_admm_iterate2<false><<<(P.n_active + 2 * T - 1) / (2 * T), T, smem, c.stream>>>(P);
             }
             CK(cudaGetLastError());

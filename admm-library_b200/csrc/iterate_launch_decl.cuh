@@ -8,10 +8,17 @@ struct IterLaunchCtx {
     int N, nb;
     bool par_batched, has_c, has_q, fast_pattern, decoupled;
     bool two_per_thread;          // use the two-problems-per-thread kernel (iterate2.cuh) when eligible
+    int kernel;                   // KV_*: pin one kernel variant (tests); KV_AUTO = pick by working-set width
+    int rows_zu;                  // rows of the compact z / u arrays
+    int device;
 };
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_pp(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 // per-problem factors staged through shared memory by TMA; false when the configuration is not eligible
 bool launch_iterate_pptma(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+// resident-tile kernel (iterate_res.cuh): iterates staged in shared memory for the whole launch; false when the
+// configuration is not eligible (per-problem factor, generic block pattern, tile larger than shared memory)
+bool launch_iterate_res(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+bool iterate_res_eligible(const IterLaunchCtx &c);
 }  // namespace admmb

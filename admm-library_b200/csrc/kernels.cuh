@@ -342,6 +342,20 @@ struct FacRef {
     }
 };
 
+// Where an iteration finds its iterates.  GlobalIO: the batch-interleaved working set in global memory, one column
+// per problem (pitch P.ld, L2-cached .cg loads / stores).  SmemIO (iterate_res.cuh): the 32-problem tile of the warp,
+// staged in shared memory for the whole launch ([row][32 lanes]).
+struct GlobalIO {
+    __device__ __forceinline__ double *z(const IterParams &P, size_t p) const { return P.z + p; }
+    __device__ __forceinline__ double *u(const IterParams &P, size_t p) const { return P.u + p; }
+    __device__ __forceinline__ double *d(const IterParams &P, size_t p) const { return P.d + p; }
+    __device__ __forceinline__ size_t pitch(const IterParams &P) const { return P.ld; }
+    // initial state s0[i] of problem p
+    __device__ __forceinline__ double s0(const IterParams &P, size_t p, int i) const { return P.s0[p + (size_t)i * P.ld]; }
+    static __device__ __forceinline__ double ld(const double *a) { return ADMMB_LD(a); }
+    static __device__ __forceinline__ void st(double *a, double v) { ADMMB_ST(a, v); }
+};
+
 __device__ __forceinline__ double2 lds128(uint32_t a)
 {
     double2 r;
@@ -550,7 +564,7 @@ __device__ __forceinline__ void fac_row3(const FacRef<FSH> &F, int k, int off, d
 
 // relaxation + prox + dual ascent + norm accumulation of one split block whose old z, u (u already
 // scaled by the pending sigma) are in registers; stores the new z, u.
-template <class ParFn>
+template <class IO = GlobalIO, class ParFn>
 __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, double alpha, double oma,
                                              const double (&xb)[3], const double (&zo)[3], const double (&uo)[3],
                                              double *zrow, double *urow, size_t ld, double &rr, double &ss,
@@ -574,24 +588,26 @@ __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, d
         zz = fma(zn[e], zn[e], zz);
         uu = fma(un, un, uu);
         if (store) {
-            ADMMB_ST(zrow + (size_t)e * ld, zn[e]);
-            ADMMB_ST(urow + (size_t)e * ld, un);
+            IO::st(zrow + (size_t)e * ld, zn[e]);
+            IO::st(urow + (size_t)e * ld, un);
         }
     }
 }
 
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT>
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, class IO = GlobalIO>
 __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const size_t p, const FacRef<FSH> F,
                                                     const int *bdesc, const uint32_t par_sbase, const double rho,
-                                                    const double sigma, double (&nr)[5])
+                                                    const double sigma, double (&nr)[5], const IO io = IO(),
+                                                    const bool act = true)
 {
     const int N = P.N;
     const size_t ld = P.ld;
     const double rinv = 1.0 / rho;
     // in this pattern the split blocks are ctrl_0 .. ctrl_{N-1} followed by the terminal blocks, so the
     // compact z/u rows of ctrl_k are 3k..3k+2: plain pointer walks, no index arithmetic in the loops
-    const ptrdiff_t ld1 = (ptrdiff_t)ld, ld2 = 2 * (ptrdiff_t)ld, ld3 = 3 * (ptrdiff_t)ld;
-    double *const zp = P.z + p, *const up = P.u + p, *const dp = P.d + p;
+    const size_t ldi = io.pitch(P);                   // pitch of the iterate rows (z, u, d)
+    const ptrdiff_t ld1 = (ptrdiff_t)ldi, ld2 = 2 * (ptrdiff_t)ldi, ld3 = 3 * (ptrdiff_t)ldi;
+    double *const zp = io.z(P, p), *const up = io.u(P, p), *const dp = io.d(P, p);
     const double *qp = HAS_Q ? (P.q_batched ? P.q + p : P.q) : nullptr;
     const size_t qld = P.q_batched ? ld : 1;
 
@@ -613,9 +629,9 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             const size_t r0 = (size_t)(de >> 8) * 3;
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                double uu = ADMMB_LD(up + (r0 + e) * ld);
+                double uu = IO::ld(up + (r0 + e) * ldi);
                 if (ADAPT) uu = uu * sigma;
-                double v = ADMMB_LD(zp + (r0 + e) * ld) - uu;
+                double v = IO::ld(zp + (r0 + e) * ldi) - uu;
                 if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
                 t[e] = v;
             }
@@ -636,12 +652,12 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     double zA[3], uA[3], zB[3], uB[3];
     {
         const double *z0 = zp + (ptrdiff_t)(N - 1) * ld3, *u0 = up + (ptrdiff_t)(N - 1) * ld3;
-        zA[0] = ADMMB_LD(z0); zA[1] = ADMMB_LD(z0 + ld1); zA[2] = ADMMB_LD(z0 + ld2);
-        uA[0] = ADMMB_LD(u0); uA[1] = ADMMB_LD(u0 + ld1); uA[2] = ADMMB_LD(u0 + ld2);
+        zA[0] = IO::ld(z0); zA[1] = IO::ld(z0 + ld1); zA[2] = IO::ld(z0 + ld2);
+        uA[0] = IO::ld(u0); uA[1] = IO::ld(u0 + ld1); uA[2] = IO::ld(u0 + ld2);
         if (N > 1) {
             z0 -= ld3; u0 -= ld3;
-            zB[0] = ADMMB_LD(z0); zB[1] = ADMMB_LD(z0 + ld1); zB[2] = ADMMB_LD(z0 + ld2);
-            uB[0] = ADMMB_LD(u0); uB[1] = ADMMB_LD(u0 + ld1); uB[2] = ADMMB_LD(u0 + ld2);
+            zB[0] = IO::ld(z0); zB[1] = IO::ld(z0 + ld1); zB[2] = IO::ld(z0 + ld2);
+            uB[0] = IO::ld(u0); uB[1] = IO::ld(u0 + ld1); uB[2] = IO::ld(u0 + ld2);
         }
     }
     const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;   // rows of stage k-2
@@ -656,8 +672,8 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             ra[e] = v;
         }
         if (k >= 2) {   // refill this buffer with the stage two steps ahead
-            zc[0] = ADMMB_LD(zl); zc[1] = ADMMB_LD(zl + ld1); zc[2] = ADMMB_LD(zl + ld2);
-            uc[0] = ADMMB_LD(ul); uc[1] = ADMMB_LD(ul + ld1); uc[2] = ADMMB_LD(ul + ld2);
+            zc[0] = IO::ld(zl); zc[1] = IO::ld(zl + ld1); zc[2] = IO::ld(zl + ld2);
+            uc[0] = IO::ld(ul); uc[1] = IO::ld(ul + ld1); uc[2] = IO::ld(ul + ld2);
         }
         zl -= ld3; ul -= ld3;
         double gg[6];
@@ -684,7 +700,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             for (int i = 0; i < 6; ++i) acc = fma(er[i], gg[i], acc);
             dj[j] = acc;
         }
-        ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]);
+        if (act) { IO::st(ds, dj[0]); IO::st(ds + ld1, dj[1]); IO::st(ds + ld2, dj[2]); }
         ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -714,16 +730,16 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
     double sA[6], sB[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) sA[i] = P.s0[p + (size_t)i * ld];
+    for (int i = 0; i < 6; ++i) sA[i] = io.s0(P, p, i);
     double dA[3], dB[3];
     {
-        zA[0] = ADMMB_LD(zp); zA[1] = ADMMB_LD(zp + ld1); zA[2] = ADMMB_LD(zp + ld2);
-        uA[0] = ADMMB_LD(up); uA[1] = ADMMB_LD(up + ld1); uA[2] = ADMMB_LD(up + ld2);
-        dA[0] = ADMMB_LD(dp); dA[1] = ADMMB_LD(dp + ld1); dA[2] = ADMMB_LD(dp + ld2);
+        zA[0] = IO::ld(zp); zA[1] = IO::ld(zp + ld1); zA[2] = IO::ld(zp + ld2);
+        uA[0] = IO::ld(up); uA[1] = IO::ld(up + ld1); uA[2] = IO::ld(up + ld2);
+        dA[0] = IO::ld(dp); dA[1] = IO::ld(dp + ld1); dA[2] = IO::ld(dp + ld2);
         if (N > 1) {
-            zB[0] = ADMMB_LD(zp + ld3); zB[1] = ADMMB_LD(zp + ld3 + ld1); zB[2] = ADMMB_LD(zp + ld3 + ld2);
-            uB[0] = ADMMB_LD(up + ld3); uB[1] = ADMMB_LD(up + ld3 + ld1); uB[2] = ADMMB_LD(up + ld3 + ld2);
-            dB[0] = ADMMB_LD(dp + ld3); dB[1] = ADMMB_LD(dp + ld3 + ld1); dB[2] = ADMMB_LD(dp + ld3 + ld2);
+            zB[0] = IO::ld(zp + ld3); zB[1] = IO::ld(zp + ld3 + ld1); zB[2] = IO::ld(zp + ld3 + ld2);
+            uB[0] = IO::ld(up + ld3); uB[1] = IO::ld(up + ld3 + ld1); uB[2] = IO::ld(up + ld3 + ld2);
+            dB[0] = IO::ld(dp + ld3); dB[1] = IO::ld(dp + ld3 + ld1); dB[2] = IO::ld(dp + ld3 + ld2);
         }
     }
     const double *zf = zp + 2 * ld3, *uf = up + 2 * ld3, *df = dp + 2 * ld3;   // rows of stage k+2 (loads)
@@ -743,17 +759,17 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             uo[j] = ADAPT ? uc[j] * sigma : uc[j];
         }
         if (k + 2 < N) {   // refill this buffer with the stage two steps ahead
-            zc[0] = ADMMB_LD(zf); zc[1] = ADMMB_LD(zf + ld1); zc[2] = ADMMB_LD(zf + ld2);
-            uc[0] = ADMMB_LD(uf); uc[1] = ADMMB_LD(uf + ld1); uc[2] = ADMMB_LD(uf + ld2);
-            dc[0] = ADMMB_LD(df); dc[1] = ADMMB_LD(df + ld1); dc[2] = ADMMB_LD(df + ld2);
+            zc[0] = IO::ld(zf); zc[1] = IO::ld(zf + ld1); zc[2] = IO::ld(zf + ld2);
+            uc[0] = IO::ld(uf); uc[1] = IO::ld(uf + ld1); uc[2] = IO::ld(uf + ld2);
+            dc[0] = IO::ld(df); dc[1] = IO::ld(df + ld1); dc[2] = IO::ld(df + ld2);
         }
         zf += ld3; uf += ld3; df += ld3;
         {
             const int b = 3 * k + 2;
             double pr[8];
             load_par(b, pr);
-            block_update(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ld, rr,
-                         ss, xx, zz, uu);
+            block_update<IO>(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ldi, rr,
+                         ss, xx, zz, uu, act);
             zw += ld3; uw += ld3;
         }
 #pragma unroll
@@ -791,13 +807,13 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
         double zo[3], uo[3], pr[8];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            zo[e] = ADMMB_LD(zp + (r0 + e) * ld);
-            double uv = ADMMB_LD(up + (r0 + e) * ld);
+            zo[e] = IO::ld(zp + (r0 + e) * ldi);
+            double uv = IO::ld(up + (r0 + e) * ldi);
             uo[e] = ADAPT ? uv * sigma : uv;
         }
         load_par(b, pr);
-        block_update(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ld,
-                     up + r0 * ld, ld, rr, ss, xx, zz, uu);
+        block_update<IO>(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ldi,
+                     up + r0 * ldi, ldi, rr, ss, xx, zz, uu, act);
     }
     nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
 }
@@ -936,18 +952,19 @@ struct NoStaging {
 
 // PD = prefetch distance in stages (even): 2 under the 128-register cap, 4 in the uncapped build, where a
 // lone warp per sub-partition has nothing else to hide the global-load latency behind.
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int PD, class Staging = NoStaging>
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, int PD, class Staging = NoStaging, class IO = GlobalIO>
 __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const size_t p, FacRef<FSH> F,
                                                    const int *bdesc, const uint32_t par_sbase, const double rho,
                                                    const double sigma, double (&nr)[5], Staging stg = Staging(),
-                                                   const bool act = true)
+                                                   const bool act = true, const IO io = IO())
 {
     stg.iter_begin(F);
     const int N = P.N;
     const size_t ld = P.ld;
     const double rinv = 1.0 / rho;
-    const ptrdiff_t ld1 = (ptrdiff_t)ld, ld2 = 2 * (ptrdiff_t)ld, ld3 = 3 * (ptrdiff_t)ld;
-    double *const zp = P.z + p, *const up = P.u + p, *const dp = P.d + p;
+    const size_t ldi = io.pitch(P);                   // pitch of the iterate rows (z, u, d)
+    const ptrdiff_t ld1 = (ptrdiff_t)ldi, ld2 = 2 * (ptrdiff_t)ldi, ld3 = 3 * (ptrdiff_t)ldi;
+    double *const zp = io.z(P, p), *const up = io.u(P, p), *const dp = io.d(P, p);
     const double *qp = HAS_Q ? (P.q_batched ? P.q + p : P.q) : nullptr;
     const size_t qld = P.q_batched ? ld : 1;
 
@@ -968,9 +985,9 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             const size_t r0 = (size_t)(de >> 8) * 3;
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                double uu = ADMMB_LD(up + (r0 + e) * ld);
+                double uu = IO::ld(up + (r0 + e) * ldi);
                 if (ADAPT) uu = uu * sigma;
-                double v = ADMMB_LD(zp + (r0 + e) * ld) - uu;
+                double v = IO::ld(zp + (r0 + e) * ldi) - uu;
                 if (HAS_Q) v = fma(-qp[(size_t)(3 * b + e) * qld], rinv, v);
                 t[e] = v;
             }
@@ -993,8 +1010,8 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     for (int t = 0; t < PD; ++t)
         if (N - 1 - t >= 0) {
             const double *z0 = zp + (ptrdiff_t)(N - 1 - t) * ld3, *u0 = up + (ptrdiff_t)(N - 1 - t) * ld3;
-            zb[t][0] = ADMMB_LD(z0); zb[t][1] = ADMMB_LD(z0 + ld1); zb[t][2] = ADMMB_LD(z0 + ld2);
-            ub[t][0] = ADMMB_LD(u0); ub[t][1] = ADMMB_LD(u0 + ld1); ub[t][2] = ADMMB_LD(u0 + ld2);
+            zb[t][0] = IO::ld(z0); zb[t][1] = IO::ld(z0 + ld1); zb[t][2] = IO::ld(z0 + ld2);
+            ub[t][0] = IO::ld(u0); ub[t][1] = IO::ld(u0 + ld1); ub[t][2] = IO::ld(u0 + ld2);
         }
     const double *zl = zp + (ptrdiff_t)(N - 1 - PD) * ld3, *ul = up + (ptrdiff_t)(N - 1 - PD) * ld3;   // stage k-PD
     double *ds = dp + (ptrdiff_t)(N - 1) * ld3;
@@ -1010,8 +1027,8 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             ra[e] = v;
         }
         if (k >= PD) {   // refill this slot with the stage PD steps ahead
-            zc[0] = ADMMB_LD(zl); zc[1] = ADMMB_LD(zl + ld1); zc[2] = ADMMB_LD(zl + ld2);
-            uc[0] = ADMMB_LD(ul); uc[1] = ADMMB_LD(ul + ld1); uc[2] = ADMMB_LD(ul + ld2);
+            zc[0] = IO::ld(zl); zc[1] = IO::ld(zl + ld1); zc[2] = IO::ld(zl + ld2);
+            uc[0] = IO::ld(ul); uc[1] = IO::ld(ul + ld1); uc[2] = IO::ld(ul + ld2);
         }
         zl -= ld3; ul -= ld3;
         double gi[4], gc[2];
@@ -1053,7 +1070,7 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
             acc = fma(er[1], gc[1], acc);
             dj[2] = acc;
         }
-        if (act) { ADMMB_ST(ds, dj[0]); ADMMB_ST(ds + ld1, dj[1]); ADMMB_ST(ds + ld2, dj[2]); }
+        if (act) { IO::st(ds, dj[0]); IO::st(ds + ld1, dj[1]); IO::st(ds + ld2, dj[2]); }
         ds -= ld3;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1112,16 +1129,16 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
     // ---------------- forward sweep.  s split the same way: si = (s0,s1,s3,s4), sc = (s2,s5)
     double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
     double siA[4], scA[2], siB[4], scB[2];
-    siA[0] = P.s0[p]; siA[1] = P.s0[p + ld]; scA[0] = P.s0[p + 2 * ld];
-    siA[2] = P.s0[p + 3 * ld]; siA[3] = P.s0[p + 4 * ld]; scA[1] = P.s0[p + 5 * ld];
+    siA[0] = io.s0(P, p, 0); siA[1] = io.s0(P, p, 1); scA[0] = io.s0(P, p, 2);
+    siA[2] = io.s0(P, p, 3); siA[3] = io.s0(P, p, 4); scA[1] = io.s0(P, p, 5);
     double db[PD][3];
 #pragma unroll
     for (int t = 0; t < PD; ++t)
         if (t < N) {
             const double *z0 = zp + (ptrdiff_t)t * ld3, *u0 = up + (ptrdiff_t)t * ld3, *d0 = dp + (ptrdiff_t)t * ld3;
-            zb[t][0] = ADMMB_LD(z0); zb[t][1] = ADMMB_LD(z0 + ld1); zb[t][2] = ADMMB_LD(z0 + ld2);
-            ub[t][0] = ADMMB_LD(u0); ub[t][1] = ADMMB_LD(u0 + ld1); ub[t][2] = ADMMB_LD(u0 + ld2);
-            db[t][0] = ADMMB_LD(d0); db[t][1] = ADMMB_LD(d0 + ld1); db[t][2] = ADMMB_LD(d0 + ld2);
+            zb[t][0] = IO::ld(z0); zb[t][1] = IO::ld(z0 + ld1); zb[t][2] = IO::ld(z0 + ld2);
+            ub[t][0] = IO::ld(u0); ub[t][1] = IO::ld(u0 + ld1); ub[t][2] = IO::ld(u0 + ld2);
+            db[t][0] = IO::ld(d0); db[t][1] = IO::ld(d0 + ld1); db[t][2] = IO::ld(d0 + ld2);
         }
     const double *zf = zp + PD * ld3, *uf = up + PD * ld3, *df = dp + PD * ld3;   // stage k+PD
     double *zw = zp, *uw = up;
@@ -1149,16 +1166,16 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
 #pragma unroll
         for (int j = 0; j < 3; ++j) { zo[j] = zc[j]; uo[j] = ADAPT ? uc[j] * sigma : uc[j]; }
         if (k + PD < N) {
-            zc[0] = ADMMB_LD(zf); zc[1] = ADMMB_LD(zf + ld1); zc[2] = ADMMB_LD(zf + ld2);
-            uc[0] = ADMMB_LD(uf); uc[1] = ADMMB_LD(uf + ld1); uc[2] = ADMMB_LD(uf + ld2);
-            dc[0] = ADMMB_LD(df); dc[1] = ADMMB_LD(df + ld1); dc[2] = ADMMB_LD(df + ld2);
+            zc[0] = IO::ld(zf); zc[1] = IO::ld(zf + ld1); zc[2] = IO::ld(zf + ld2);
+            uc[0] = IO::ld(uf); uc[1] = IO::ld(uf + ld1); uc[2] = IO::ld(uf + ld2);
+            dc[0] = IO::ld(df); dc[1] = IO::ld(df + ld1); dc[2] = IO::ld(df + ld2);
         }
         zf += ld3; uf += ld3; df += ld3;
         {
             const int b = 3 * k + 2;
             double pr[8];
             load_par(b, pr);
-            block_update(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ld, rr,
+            block_update<IO>(bdesc[b] & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, a, zo, uo, zw, uw, ldi, rr,
                          ss, xx, zz, uu, act);
             zw += ld3; uw += ld3;
         }
@@ -1223,13 +1240,13 @@ __device__ __forceinline__ void admm_iteration_dec(const IterParams &P, const si
         double zo[3], uo[3], pr[8];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-            zo[e] = ADMMB_LD(zp + (r0 + e) * ld);
-            double uv = ADMMB_LD(up + (r0 + e) * ld);
+            zo[e] = IO::ld(zp + (r0 + e) * ldi);
+            double uv = IO::ld(up + (r0 + e) * ldi);
             uo[e] = ADAPT ? uv * sigma : uv;
         }
         load_par(b, pr);
-        block_update(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ld,
-                     up + r0 * ld, ld, rr, ss, xx, zz, uu, act);
+        block_update<IO>(de & 0xff, [&](int q) { return pr[q]; }, rinv, P.alpha, P.oma, xb, zo, uo, zp + r0 * ldi,
+                     up + r0 * ldi, ldi, rr, ss, xx, zz, uu, act);
     }
     nr[0] = rr; nr[1] = ss; nr[2] = xx; nr[3] = zz; nr[4] = uu;
 }

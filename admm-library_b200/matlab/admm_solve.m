@@ -14,6 +14,7 @@ function [x, z, u, hist] = admm_solve(prob, opts)
 %   prob.z0, prob.u0 [n x Bsz], prob.rho0 [Bsz]                                    (optional warm start)
 %   opts: rho alpha abstol reltol max_iter adapt_rho adapt_mu adapt_tau adapt_every adapt_until
 %         xupdate ('auto'|'dense'|'riccati') precision ('fp64'|'tf32') history gpus chunk
+%         kernel (0 = auto; ADMMB_KERNEL_* code, tests only) tf32_switch tf32_refresh (0 = defaults)
 %         precision 'fp64' (default): results bit-identical to the oracle admm_ocp.m order of operations.
 %         precision 'tf32': the tensor cores may be used (x-update increments as TF32x3 GEMMs, FP64 accumulation) --
 %         with xupdate 'dense' throughout, with 'auto' once few problems are still running; results then follow the
@@ -30,7 +31,8 @@ function [x, z, u, hist] = admm_solve(prob, opts)
     if nargin < 2, opts = struct(); end
     d = struct('rho', 1.0, 'alpha', 1.0, 'abstol', 1e-6, 'reltol', 1e-6, 'max_iter', 1000, ...
                'adapt_rho', 0, 'adapt_mu', 10.0, 'adapt_tau', 2.0, 'adapt_every', 25, 'adapt_until', 0, ...
-               'xupdate', 'auto', 'precision', 'fp64', 'history', 0, 'gpus', 0, 'chunk', 0);
+               'xupdate', 'auto', 'precision', 'fp64', 'history', 0, 'gpus', 0, 'chunk', 0, ...
+               'kernel', 0, 'tf32_switch', 0, 'tf32_refresh', 0);
     f = fieldnames(d);
     for i = 1:numel(f)
         if ~isfield(opts, f{i}), opts.(f{i}) = d.(f{i}); end

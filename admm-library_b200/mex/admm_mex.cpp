@@ -150,6 +150,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     op.precision = opt_enum(O, "precision", pr, 2, ADMMB_PREC_FP64);
     op.history = (int32_t)opt_scalar(O, "history", 0);
     op.chunk = (int32_t)opt_scalar(O, "chunk", 0);
+    op.kernel = (int32_t)opt_scalar(O, "kernel", 0);
+    op.tf32_switch = (int32_t)opt_scalar(O, "tf32_switch", 0);
+    op.tf32_refresh = (int32_t)opt_scalar(O, "tf32_refresh", 0);
     const int gpus = (int)opt_scalar(O, "gpus", 0);
 
     // ---- handle: created once, kept across calls (CUDA context, device buffers, worker threads)

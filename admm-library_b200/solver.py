@@ -16,6 +16,9 @@ XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
 # tf32: tensor cores allowed (3xTF32 split GEMM on the x-update increments; with xupdate="dense" throughout, with
 # "auto" once the working set is narrow); tf32_single: unit entry point only
 PRECISION = {"fp64": 0, "tf32": 1, "tf32_single": 2}
+# kernel variant of the FP64 Riccati path (include/admm_b200.h ADMMB_KERNEL_*): "auto" in normal use
+KERNEL = {"auto": 0, "thread": 1, "thread_wide": 2, "thread2": 3, "tile": 4, "wg": 5}
+DEFAULT_KERNEL = "auto"   # what make_opts uses when opts has no "kernel" key (the GPU test suite pins each variant in turn)
 FS = 156  # doubles per stage in a factor record (csrc/common.cuh)
 # name -> (offset, rows, cols, row stride) inside one record
 FAC_LAYOUT = dict(K=(0, 3, 6, 6), Acl=(18, 6, 6, 6), Hinv=(54, 3, 3, 4), E=(66, 3, 6, 6), A=(84, 6, 6, 6),
@@ -84,7 +87,9 @@ def make_opts(opts: dict) -> L.Opts:
                   adapt_mu=float(opts.get("adapt_mu", 10.0)), adapt_tau=float(opts.get("adapt_tau", 2.0)),
                   adapt_every=int(opts.get("adapt_every", 25)), adapt_until=int(opts.get("adapt_until", 0)),
                   xupdate=XUPDATE[opts.get("xupdate", "auto")], precision=PRECISION[opts.get("precision", "fp64")],
-                  history=int(opts.get("history", 0)), chunk=int(opts.get("chunk", 0)))
+                  history=int(opts.get("history", 0)), chunk=int(opts.get("chunk", 0)),
+                  kernel=KERNEL[opts.get("kernel", DEFAULT_KERNEL)], tf32_switch=int(opts.get("tf32_switch", 0)),
+                  tf32_refresh=int(opts.get("tf32_refresh", 0)))
 
 
 class ResultBuffers:

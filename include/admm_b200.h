@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ADMMB_VERSION 100
+#define ADMMB_VERSION 200
 
 /* return codes */
 enum {
@@ -67,6 +67,18 @@ enum { ADMMB_ST_CONVERGED = 0, ADMMB_ST_MAX_ITER = 1, ADMMB_ST_NAN = 2 };
 enum { ADMMB_XUPDATE_AUTO = 0, ADMMB_XUPDATE_DENSE = 1, ADMMB_XUPDATE_RICCATI = 2 };
 enum { ADMMB_PREC_FP64 = 0, ADMMB_PREC_TF32 = 1 };   /* TF32: tensor cores allowed -- with XUPDATE_DENSE throughout, with
                                                         XUPDATE_AUTO once the working set is narrow; not with RICCATI */
+
+/* kernel selection of the FP64 Riccati path.  AUTO in normal use (the library picks by working-set width); the other
+ * codes pin one variant so that tests can hold EVERY variant against the oracle at any batch size.  A variant that
+ * is not applicable to the problem (e.g. TILE with per-problem models) falls back to AUTO's choice. */
+enum {
+    ADMMB_KERNEL_AUTO = 0,
+    ADMMB_KERNEL_THREAD = 1,       /* one problem per thread, 128-register build, two CTAs per SM            */
+    ADMMB_KERNEL_THREAD_WIDE = 2,  /* one problem per thread, uncapped registers, deeper prefetch            */
+    ADMMB_KERNEL_THREAD2 = 3,      /* two problems per thread (full-width working sets)                      */
+    ADMMB_KERNEL_TILE = 4,         /* resident tile: one warp per 32 problems, iterates in shared memory     */
+    ADMMB_KERNEL_WG = 5            /* warp group: four role-split warps per 32-problem resident tile         */
+};
 
 typedef struct admmb_ctx *admmb_handle;
 
@@ -102,6 +114,11 @@ typedef struct admmb_opts {
     int32_t precision;           /* ADMMB_PREC_*                                                */
     int32_t history;             /* record per-iteration r,s,eps,rho                            */
     int32_t chunk;               /* iterations per persistent launch (0 = library default)     */
+    int32_t kernel;              /* ADMMB_KERNEL_* (0 = auto)                                   */
+    int32_t tf32_switch;         /* precision = TF32, xupdate = auto: running problems at which the tensor-core
+                                    pair takes over from the FP64 Riccati kernel (0 = default 8192; < 0 = never) */
+    int32_t tf32_refresh;        /* TF32 path: iterations between exact FP64 refreshes of x (0 = default 1000;
+                                    < 0 = never)                                                 */
 } admmb_opts;
 
 /* outputs; every pointer is caller-allocated and may be NULL when that output is not wanted */

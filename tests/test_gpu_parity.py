@@ -8,11 +8,43 @@ from conftest import assert_bit_identical
 
 pytestmark = pytest.mark.gpu
 
+# Every test of this file runs once per kernel variant of the FP64 Riccati path (include/admm_b200.h ADMMB_KERNEL_*):
+# "auto" is what a user gets; the others pin the register-capped / uncapped one-problem-per-thread builds, the
+# two-problems-per-thread kernel, the resident-tile kernel and the warp-group kernel at ANY batch size, so the variants
+# that a benchmark-sized batch selects are held against the oracle too (a pinned variant that does not apply to a
+# problem -- e.g. the tile kernel with per-problem models -- falls back to the automatic choice).
+VARIANTS = ["auto", "thread", "thread_wide", "thread2", "tile", "wg"]
+
+
+@pytest.fixture(autouse=True, params=VARIANTS)
+def kernel_variant(request, pkg):
+    pkg.solver.DEFAULT_KERNEL = request.param
+    yield request.param
+    pkg.solver.DEFAULT_KERNEL = "auto"
+
+
+_REF_CACHE = {}
+
+
+def _key(prob, opts):
+    import hashlib
+    h = hashlib.sha1()
+    for k in sorted(prob):
+        v = prob[k]
+        if isinstance(v, np.ndarray):
+            h.update(k.encode()); h.update(str(v.shape).encode()); h.update(np.ascontiguousarray(v).tobytes())
+        elif v is not None and not isinstance(v, dict):
+            h.update(f"{k}={v}".encode())
+    h.update(repr(sorted((k, v) for k, v in opts.items() if k not in ("kernel", "chunk"))).encode())
+    return h.hexdigest()
+
 
 def _both(solver, cpu_oracle, prob, opts):
     got = solver.solve(prob, opts)
-    ref = cpu_oracle.solve(prob, opts)
-    return got, ref
+    k = _key(prob, opts)
+    if k not in _REF_CACHE:                      # the oracle result does not depend on the kernel variant
+        _REF_CACHE[k] = cpu_oracle.solve(prob, opts)
+    return got, _REF_CACHE[k]
 
 
 def test_cfg1_single_problem_history(solver, cpu_oracle, P):
@@ -175,12 +207,14 @@ def test_two_gpus_in_one_process_match_one_gpu(pkg, cpu_oracle, P):
     assert_bit_identical(got, ref, "two GPUs, one process")
     assert got[3]["stats"][:3] == [int(v) for v in ref[3]["stats"][:3]]
 
-def test_two_gpus_in_one_process_tf32_path(pkg, solver, P):
+def test_two_gpus_in_one_process_tf32_path(pkg, solver, P, kernel_variant):
     """The tensor-core path under the in-process two-GPU deployment: each worker thread captures and replays its own
     CUDA graphs and sets its own device's kernel attributes.  Unlike the FP64 path this one is NOT invariant to how
     the batch is sharded (the number of threads per problem -- hence the summation order of the norms -- and the
     iteration at which x_R is refreshed depend on the width of the working set), so the comparison with the one-GPU
     run is within the path's precision class, not bitwise."""
+    if kernel_variant != "auto":
+        pytest.skip("the tensor-core path does not depend on the FP64 kernel variant")
     try:
         s2 = pkg.Solver(devices=[0, 1])
     except pkg.AdmmError:
