@@ -320,8 +320,10 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
                     rows_zu, device};
     last_kernel = KV_THREAD;
     if (FSH && FSMEM) {
-        const bool tile = kernel_variant == KV_TILE || (kernel_variant == KV_AUTO && P.n_active <= tile_width);
-        if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
+        const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && P.n_active <= tile_width);
+        const bool tile = kernel_variant == KV_TILE;
+        if (wg && launch_iterate_wg(c, P, adapt)) last_kernel = KV_WG;
+        else if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
         else launch_iterate_smem(c, P, adapt);
     }
     else if (FSH) launch_iterate_gshared(c, P, adapt);

@@ -1,0 +1,57 @@
+// iter_wg.cu -- launcher of the warp-group kernel (iterate_wg.cuh): tile width from the shared-memory budget,
+// grid = one CTA per resident tile (persistent over tiles when there are more tiles than SMs).
+#include <cstdlib>
+#include "host_util.cuh"
+#define ADMMB_ITERATE_ONLY
+#include "iterate_wg.cuh"
+#include "iterate_launch_decl.cuh"
+
+namespace admmb {
+
+namespace {
+constexpr size_t WG_SMEM_MAX = 227 * 1024;      // opt-in dynamic shared memory per CTA on sm_100
+
+struct WgAttr { const void *kern; int device; size_t smem; };
+
+template <class K>
+void wg_set_attr(K kern, size_t smem, int device)
+{
+    static thread_local WgAttr done[8];
+    static thread_local int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (done[i].kern == (const void *)kern && done[i].device == device && done[i].smem >= smem) return;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (used == 8) used = 0;
+    done[used++] = WgAttr{(const void *)kern, device, smem};
+}
+}  // namespace
+
+// widest tile (problems per CTA, <= 32) whose z, u, d, g rows fit next to the factor; 0: not eligible
+int iterate_wg_tile_width(const IterLaunchCtx &c)
+{
+    if (!c.fast_pattern || !c.decoupled || c.has_c || c.has_q || c.par_batched || c.rows_zu <= 0) return 0;
+    for (int tw = 32; tw >= WG_MIN_TW; --tw)
+        if (wg_layout(c.N, c.rows_zu, tw).total <= WG_SMEM_MAX) return tw;
+    return 0;
+}
+
+// shared factor only (the caller checks)
+bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt)
+{
+    const int tw = iterate_wg_tile_width(c);
+    if (tw == 0) return false;
+    const size_t smem = wg_layout(c.N, c.rows_zu, tw).total;
+    const int ntiles = (P.n_active + tw - 1) / tw;
+    const int grid = ntiles < c.num_sms ? ntiles : c.num_sms;
+    if (adapt) {
+        wg_set_attr(k_admm_iterate_wg<true>, smem, c.device);
+        k_admm_iterate_wg<true><<<grid, WG_WARPS * 32, smem, c.stream>>>(P, tw);
+    } else {
+        wg_set_attr(k_admm_iterate_wg<false>, smem, c.device);
+        k_admm_iterate_wg<false><<<grid, WG_WARPS * 32, smem, c.stream>>>(P, tw);
+    }
+    CK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace admmb

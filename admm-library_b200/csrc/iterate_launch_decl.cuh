@@ -21,4 +21,8 @@ bool launch_iterate_pptma(const IterLaunchCtx &c, const IterParams &P, bool adap
 // configuration is not eligible (per-problem factor, generic block pattern, tile larger than shared memory)
 bool launch_iterate_res(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 bool iterate_res_eligible(const IterLaunchCtx &c);
+// warp-group kernel (iterate_wg.cuh): eight warps per resident tile; false when not eligible (needs the decoupled
+// shared factor, the fast block pattern, no affine term / linear cost / per-problem parameters)
+bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+int iterate_wg_tile_width(const IterLaunchCtx &c);
 }  // namespace admmb

@@ -35,14 +35,11 @@ struct SmemIO {
     __device__ __forceinline__ double *d(const IterParams &, size_t) const { return ds; }
     __device__ __forceinline__ size_t pitch(const IterParams &) const { return 32; }
     __device__ __forceinline__ double s0(const IterParams &, size_t, int i) const { return ld(s0s + 32 * i); }
-    static __device__ __forceinline__ double ld(const double *a)
-    {
-        return lds64((uint32_t)__cvta_generic_to_shared(a));
-    }
-    static __device__ __forceinline__ void st(double *a, double v)
-    {
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(a)), "d"(v) : "memory");
-    }
+    // plain accesses: the pointers derive from the kernel's shared array, so they compile to LDS.64 / STS.64, and the
+    // compiler sees the loads and stores as memory operations (an asm load without a memory operand would be hoisted
+    // out of the iteration loop as loop-invariant)
+    static __device__ __forceinline__ double ld(const double *a) { return *a; }
+    static __device__ __forceinline__ void st(double *a, double v) { *a = v; }
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar)

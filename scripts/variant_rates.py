@@ -11,7 +11,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 max_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 widths = [int(w) for w in (sys.argv[4] if len(sys.argv) > 4 else "1024,4096,8192,16384,65536").split(",")]
-variants = (sys.argv[5] if len(sys.argv) > 5 else "thread,thread_wide,thread2,tile").split(",")
+variants = (sys.argv[5] if len(sys.argv) > 5 else "thread_wide,thread2,tile,wg").split(",")
 pkg = graft.load_pkg()
 P = pkg.problems
 gen = {"cfg2": P.cfg2_cw_batch, "cfg3": P.cfg3_lowthrust_soc, "cfg5": P.cfg5_montecarlo}[name]
