@@ -9,13 +9,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "admm_b200.cu")
 # translation units: the host library + three thirds of the persistent-kernel template variants
 UNITS = ["admm_b200.cu", "iter_smem.cu", "iter_gshared.cu", "iter_pp.cu", "iter_pptma.cu", "iter_res.cu", "iter_wg.cu"]
-OUT_DIR = os.path.join(HERE, "lib")
+OUT_DIR = os.path.join(HERE, os.environ.get("ADMMB_BUILD_DIR", "lib"))   # developer builds may go elsewhere
 OUT = os.path.join(OUT_DIR, "libadmm_b200.so")
 
 NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17",
               # explicit fma() only: the operation order written in the kernels is the one executed
               "-fmad=false"]
+# developer builds only (e.g. ADMMB_EXTRA_NVCC_FLAGS=-DWG_TIMING prints a per-warp cycle timeline of one iteration)
+NVCC_FLAGS += os.environ.get("ADMMB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources() -> list[str]:

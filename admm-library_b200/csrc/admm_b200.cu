@@ -91,6 +91,7 @@ struct Shard {
     int kernel_variant = KV_AUTO;  // opts.kernel of the current run (ADMMB_KERNEL_*)
     int last_kernel = KV_THREAD;   // what the last launch ran
     bool decoupled = false;      // in-plane / cross-track structure proven on the factor: packed records
+    bool time_invariant = false; // shared model with A_k, B_k bitwise equal for every stage (the warp-group kernel keeps them in registers)
     int max_iter_alloc = 0;
     bool hist_alloc = false;
 
@@ -247,6 +248,11 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
                     controls_split && !op->adapt_rho && !op->history && getenv("ADMMB_NO_TF32_TAIL") == nullptr;
     }
 
+    time_invariant = !dyn_batched;
+    for (int k = 1; k < N && time_invariant; ++k)
+        time_invariant = memcmp(pb->A, pb->A + (size_t)36 * k, 36 * sizeof(double)) == 0 &&
+                         memcmp(pb->B, pb->B + (size_t)18 * k, 18 * sizeof(double)) == 0;
+
     // raw model
     const size_t md = dyn_batched ? ld : 1;
     auto up_model = [&](DevBuf<double> &buf, const double *host, int R) {
@@ -317,7 +323,7 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
     // widest working set the resident-tile kernel takes when the choice is the library's (tuning knob; no effect on results)
     static const int64_t tile_width = getenv("ADMMB_TILE_WIDTH") ? atoll(getenv("ADMMB_TILE_WIDTH")) : 16384;
     IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default, kernel_variant,
-                    rows_zu, device};
+                    rows_zu, device, time_invariant};
     last_kernel = KV_THREAD;
     if (FSH && FSMEM) {
         const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && P.n_active <= tile_width);

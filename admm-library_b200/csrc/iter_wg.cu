@@ -43,13 +43,14 @@ bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt)
     const size_t smem = wg_layout(c.N, c.rows_zu, tw).total;
     const int ntiles = (P.n_active + tw - 1) / tw;
     const int grid = ntiles < c.num_sms ? ntiles : c.num_sms;
-    if (adapt) {
-        wg_set_attr(k_admm_iterate_wg<true>, smem, c.device);
-        k_admm_iterate_wg<true><<<grid, WG_WARPS * 32, smem, c.stream>>>(P, tw);
-    } else {
-        wg_set_attr(k_admm_iterate_wg<false>, smem, c.device);
-        k_admm_iterate_wg<false><<<grid, WG_WARPS * 32, smem, c.stream>>>(P, tw);
-    }
+#define WG_LAUNCH(A, T)                                                                   \
+    do {                                                                                  \
+        wg_set_attr(k_admm_iterate_wg<A, T>, smem, c.device);                             \
+        k_admm_iterate_wg<A, T><<<grid, WG_WARPS * 32, smem, c.stream>>>(P, tw);          \
+    } while (0)
+    if (adapt) { if (c.time_invariant) WG_LAUNCH(true, true); else WG_LAUNCH(true, false); }
+    else { if (c.time_invariant) WG_LAUNCH(false, true); else WG_LAUNCH(false, false); }
+#undef WG_LAUNCH
     CK(cudaGetLastError());
     return true;
 }

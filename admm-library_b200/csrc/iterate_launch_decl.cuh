@@ -11,6 +11,7 @@ struct IterLaunchCtx {
     int kernel;                   // KV_*: pin one kernel variant (tests); KV_AUTO = pick by working-set width
     int rows_zu;                  // rows of the compact z / u arrays
     int device;
+    bool time_invariant;          // shared model whose A_k, B_k are the same for every stage (bitwise)
 };
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);

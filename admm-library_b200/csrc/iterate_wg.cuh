@@ -13,8 +13,8 @@
 //   warps 2, 3, 6, 7  PROX      trail the forward sweep stage by stage: relaxation, prox and dual ascent of control block k
 //                               as soon as both chain warps have published a_k (one mbarrier per stage), then the terminal
 //                               blocks; z+ - z is left in g for the norms.
-//   warp 5  NORMS               trails the prox warps block by block: the five norm accumulators, each summed over the
-//                               blocks in the oracle's order.
+//   warp 5  NORMS               trails the prox warps block by block (polling their progress counters): the five norm
+//                               accumulators, each summed over the blocks in the oracle's order.
 //   warp 4                      shares its sub-partition with the in-plane chain and stays out of its way (tile I/O only).
 // One CTA-wide barrier per iteration (before the stopping test); every warp then evaluates the test for its lane
 // (identical arithmetic, no broadcast needed).  The per-stage hand-over uses mbarriers (arrive.release by one elected lane
@@ -25,6 +25,9 @@
 // Scope: shared decoupled factor (CW / Yamanaka-Ankersen structure, checked on the factor), "states unsplit, controls
 // split" pattern, no affine term, no linear cost, shared parameter table: the pattern of BASELINE configs 1, 2, 3, 5.
 #pragma once
+#ifdef WG_TIMING
+#include <cstdio>
+#endif
 #include "kernels.cuh"
 
 namespace admmb {
@@ -36,7 +39,7 @@ constexpr int WG_PROX = 4;                       // prox warps
 struct WgLayout {                                // byte offsets inside the dynamic shared memory of one CTA
     int TW;                                      // tile width: problems per CTA
     int rz, rd, rg;                              // doubles per problem in the z / u, d and g arrays (odd: see below)
-    size_t bars, fac, par, typ, z, u, d, g, s0, nrm, total;
+    size_t bars, prog, fac, par, typ, z, u, d, g, s0, nrm, total;
 };
 
 // Tile arrays are stored PROBLEM-major: the rows of one problem are contiguous, lane p starts at p * pitch.  A row is
@@ -51,8 +54,9 @@ __host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW)
     L.rg = (6 * N + 12) | 1;                     // per stage a_k (3) + ds_k (3); then s_N (6) and the terminal ds (6)
     const int nsb = rows_zu / 3;                 // split blocks: N controls + the split terminal blocks
     size_t o = 16;                               // [0, 8): mbarrier of the factor copy
-    L.bars = o; o += 8 * (size_t)(2 * N + 2);    // bC2[0..N] (a_k / s_N published), bP3[0..N] (block k / terminal blocks done)
+    L.bars = o; o += 8 * (size_t)(N + 1);        // bC2[0..N]: a_k / s_N published by both chain warps
     o = (o + 15) / 16 * 16;
+    L.prog = o; o += 16;                         // blocks finished by each prox warp since the launch began (4 x u32)
     L.fac = o; o += sizeof(double) * FD * (size_t)N;
     L.par = o; o += sizeof(double) * 8 * (size_t)nsb;          // parameter table, compact: one record per split block
     L.typ = o; o += sizeof(int) * (size_t)((nsb + 3) / 4 * 4);
@@ -62,7 +66,7 @@ __host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW)
     L.d = o; o += col * L.rd;
     L.g = o; o += col * L.rg;
     L.s0 = o; o += col * 7;
-    L.nrm = o; o += col * 10;                    // two sets of five, alternating by iteration parity
+    L.nrm = o; o += col * 15;                    // two sets of five sums, alternating by iteration parity; five roots
     L.total = (o + 15) / 16 * 16;
     return L;
 }
@@ -109,6 +113,20 @@ __device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity)
     } while (!ok);
 }
 
+// Same hand-over, polled with test_wait: a try_wait that has to block suspends the warp and wakes it up late; the prox warps
+// sit right behind the chain, where that wake-up latency goes straight into the length of an iteration.
+__device__ __forceinline__ void wg_wait_spin(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    int spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1 << 24)) __trap();
+    } while (!ok);
+}
+
 // Stage loop with the operands of the next stage loaded (into registers) BEFORE the current stage's arithmetic and
 // stores: a warp issues in order, so without this every stage would start by waiting out its own load latency.
 // Stage j = 0 .. count-1 is k = k0 + j * stride.  Branch-free body: the prefetch past the end re-reads the last stage.
@@ -129,7 +147,20 @@ __device__ __forceinline__ void wg_stage_loop(const int k0, const int stride, co
     if (count & 1) work(klast, a);
 }
 
-template <bool ADAPT>
+#ifdef WG_TIMING
+// developer build: absolute SM-clock stamps of one iteration (the 8th of the launch) of CTA 0, printed when the launch ends
+__device__ long long wg_tlog[WG_WARPS][8];
+__device__ long long wg_klog[3][64];               // per stage: a_k published (in-plane chain), block k done (prox), block k accumulated
+#define WG_T(idx) do { if (blockIdx.x == 0 && (tid & 31) == 0 && cnt == 7) wg_tlog[warp][idx] = clock64(); } while (0)
+#define WG_TK(row, k) do { if (blockIdx.x == 0 && (tid & 31) == 0 && cnt == 7 && (k) < 64) wg_klog[row][k] = clock64(); } while (0)
+#else
+#define WG_T(idx) do { } while (0)
+#define WG_TK(row, k) do { } while (0)
+#endif
+
+// TI: A_k, B_k do not depend on the stage (time-invariant dynamics, e.g. Clohessy-Wiltshire with a fixed step): the chain
+// warps keep them in registers for the whole launch instead of re-reading 30 doubles per stage on the forward sweep
+template <bool ADAPT, bool TI>
 __global__ void __launch_bounds__(WG_WARPS * 32, 1)
 k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
 {
@@ -142,7 +173,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     const int lane = min(tid & 31, TW - 1);
     const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(wg_smem);
     const uint32_t mbar = sm0;
-    const uint32_t bC2 = sm0 + (uint32_t)L.bars, bP3 = bC2 + 8u * (uint32_t)(N + 1);
+    const uint32_t bC2 = sm0 + (uint32_t)L.bars, prog_s = sm0 + (uint32_t)L.prog;
     const uint32_t fac_s = sm0 + (uint32_t)L.fac, par_s = sm0 + (uint32_t)L.par, typ_s = sm0 + (uint32_t)L.typ;
     // this lane's problem in every tile array (byte addresses; row r of an array is at base + 8 r)
     const uint32_t zs = sm0 + (uint32_t)L.z + (uint32_t)(lane * L.rz) * 8u;
@@ -150,7 +181,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     const uint32_t ds = sm0 + (uint32_t)L.d + (uint32_t)(lane * L.rd) * 8u;
     const uint32_t gs = sm0 + (uint32_t)L.g + (uint32_t)(lane * L.rg) * 8u;
     const uint32_t s0s = sm0 + (uint32_t)L.s0 + (uint32_t)(lane * 7) * 8u;
-    const uint32_t nrs0 = sm0 + (uint32_t)L.nrm + (uint32_t)(lane * 10) * 8u;
+    const uint32_t nrs0 = sm0 + (uint32_t)L.nrm + (uint32_t)(lane * 15) * 8u;
     const uint32_t gN = gs + (uint32_t)(6 * N) * 8u;      // s_N in natural order (6 rows), then the terminal blocks' ds (6 rows)
 
     // roles
@@ -160,10 +191,8 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     // ---- once per CTA: factor (one TMA bulk copy), hand-over barriers, compact parameter table and block types
     if (tid == 0) {
         mbar_init(mbar, 1);
-        for (int k = 0; k <= N; ++k) {
-            mbar_init(bC2 + 8u * k, 2);                       // both chain warps
-            mbar_init(bP3 + 8u * k, k < N ? 1 : 2);           // the prox warp of block k; the two terminal blocks
-        }
+        for (int k = 0; k <= N; ++k) mbar_init(bC2 + 8u * k, 2);      // both chain warps
+        for (int w = 0; w < WG_PROX; ++w) asm volatile("st.shared.u32 [%0], %1;" ::"r"(prog_s + 4u * w), "r"(0) : "memory");
         mbar_expect_tx(mbar, (uint32_t)(FD * N * 8));
         bulk_g2s(fac_s, P.fac_dec, (uint32_t)(FD * N * 8), mbar);
     }
@@ -184,9 +213,25 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     __syncthreads();
     mbar_wait(mbar, 0);
 
+    double Ai[4][4], Bi[4][2], Ac[2][2], Bc[2];          // TI: the stage-invariant dynamics of this warp's chain
+    if (TI && chain_in) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            wg_ld4(fac_s + (D_AIN + 4 * r) * 8, Ai[r]);
+            wg_ld2(fac_s + (D_BIN + 2 * r) * 8, Bi[r][0], Bi[r][1]);
+        }
+    }
+    if (TI && chain_c) {
+        wg_ld2(fac_s + D_AC * 8, Ac[0][0], Ac[0][1]);
+        wg_ld2(fac_s + (D_AC + 2) * 8, Ac[1][0], Ac[1][1]);
+        wg_ld2(fac_s + D_BC * 8, Bc[0], Bc[1]);
+    }
+
     const size_t ld = P.ld;
     const int ntiles = (P.n_active + TW - 1) / TW;
     uint32_t ph = 0;                                     // parity of the hand-over barriers: flips once per iteration
+    uint32_t pcount = 0;                                 // prox warps: blocks finished since the launch began
+    uint32_t nbase[WG_PROX] = {0, 0, 0, 0};              // norm warp: the prox warps' counts when the current iteration began
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * TW + lane;
         const bool valid = t < P.n_active;
@@ -223,6 +268,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
             // norm slots of this iteration (the other set may still be read by a warp that is late in the previous
             // iteration's stopping test)
             const uint32_t nrs = nrs0 + 40u * ph;
+            WG_T(0);
 
             if (chain_in) {
                 // ================= in-plane chain: states (s0, s1, s3, s4), controls (a0, a1)
@@ -292,6 +338,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                             for (int i = 0; i < 4; ++i) gi[i] = pi[i];
                         });
                 }
+                WG_T(1);
                 // ---- forward sweep: a_k = d_k + K_k s_k (published for the prox warps), s_{k+1} = A_k s_k + B_k a_k
                 double si[4] = {wg_ld(s0s), wg_ld(s0s + 8), wg_ld(s0s + 24), wg_ld(s0s + 32)};
                 {
@@ -301,10 +348,12 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                             const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u, dk = ds + (uint32_t)(3 * k) * 8u;
                             wg_ld4(fk + D_KIN * 8, o.kn[0]);
                             wg_ld4(fk + (D_KIN + 4) * 8, o.kn[1]);
+                            if (!TI) {
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                wg_ld4(fk + (D_AIN + 4 * r) * 8, o.an[r]);
-                                wg_ld2(fk + (D_BIN + 2 * r) * 8, o.bn[r][0], o.bn[r][1]);
+                                for (int r = 0; r < 4; ++r) {
+                                    wg_ld4(fk + (D_AIN + 4 * r) * 8, o.an[r]);
+                                    wg_ld2(fk + (D_BIN + 2 * r) * 8, o.bn[r][0], o.bn[r][1]);
+                                }
                             }
                             o.d[0] = wg_ld(dk);
                             o.d[1] = wg_ld(dk + 8);
@@ -317,15 +366,18 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                             wg_st(gk, a0);
                             wg_st(gk + 8, a1);
                             wg_arrive(bC2 + 8u * k);
+                            WG_TK(0, k);
+                            const auto &an = TI ? Ai : o.an;
+                            const auto &bn = TI ? Bi : o.bn;
                             double ni[4];
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
-                                double acc = o.an[r][0] * si[0];
-                                acc = fma(o.an[r][1], si[1], acc);
-                                acc = fma(o.an[r][2], si[2], acc);
-                                acc = fma(o.an[r][3], si[3], acc);
-                                acc = fma(o.bn[r][0], a0, acc);
-                                acc = fma(o.bn[r][1], a1, acc);
+                                double acc = an[r][0] * si[0];
+                                acc = fma(an[r][1], si[1], acc);
+                                acc = fma(an[r][2], si[2], acc);
+                                acc = fma(an[r][3], si[3], acc);
+                                acc = fma(bn[r][0], a0, acc);
+                                acc = fma(bn[r][1], a1, acc);
                                 ni[r] = acc;
                             }
 #pragma unroll
@@ -334,6 +386,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                 }
                 wg_st(gN, si[0]); wg_st(gN + 8, si[1]); wg_st(gN + 24, si[2]); wg_st(gN + 32, si[3]);   // s_N, natural order
                 wg_arrive(bC2 + 8u * N);
+                WG_T(2);
             } else if (chain_c) {
                 // ================= cross-track chain: states (s2, s5), control a2
                 double gc0 = 0.0, gc1 = 0.0;
@@ -375,6 +428,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                             gc0 = p0; gc1 = p1;
                         });
                 }
+                WG_T(1);
                 double sc0 = wg_ld(s0s + 16), sc1 = wg_ld(s0s + 40);
                 {
                     struct In { double kc[2], a0[2], a1[2], bc[2], d2; };
@@ -382,9 +436,11 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                         [&](int k, In &in) {
                             const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u;
                             wg_ld2(fk + D_KC * 8, in.kc[0], in.kc[1]);
-                            wg_ld2(fk + D_AC * 8, in.a0[0], in.a0[1]);
-                            wg_ld2(fk + (D_AC + 2) * 8, in.a1[0], in.a1[1]);
-                            wg_ld2(fk + D_BC * 8, in.bc[0], in.bc[1]);
+                            if (!TI) {
+                                wg_ld2(fk + D_AC * 8, in.a0[0], in.a0[1]);
+                                wg_ld2(fk + (D_AC + 2) * 8, in.a1[0], in.a1[1]);
+                                wg_ld2(fk + D_BC * 8, in.bc[0], in.bc[1]);
+                            }
                             in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
                         },
                         [&](int k, const In &in) {
@@ -392,34 +448,40 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                             a2 = fma(in.kc[1], sc1, a2);
                             wg_st(gs + (uint32_t)(6 * k + 2) * 8u, a2);
                             wg_arrive(bC2 + 8u * k);
-                            double n0 = in.a0[0] * sc0;
-                            n0 = fma(in.a0[1], sc1, n0);
-                            n0 = fma(in.bc[0], a2, n0);
-                            double n1 = in.a1[0] * sc0;
-                            n1 = fma(in.a1[1], sc1, n1);
-                            n1 = fma(in.bc[1], a2, n1);
+                            const auto &a0r = TI ? Ac[0] : in.a0;
+                            const auto &a1r = TI ? Ac[1] : in.a1;
+                            const auto &bcr = TI ? Bc : in.bc;
+                            double n0 = a0r[0] * sc0;
+                            n0 = fma(a0r[1], sc1, n0);
+                            n0 = fma(bcr[0], a2, n0);
+                            double n1 = a1r[0] * sc0;
+                            n1 = fma(a1r[1], sc1, n1);
+                            n1 = fma(bcr[1], a2, n1);
                             sc0 = n0; sc1 = n1;
                         });
                 }
                 wg_st(gN + 16, sc0); wg_st(gN + 40, sc1);
                 wg_arrive(bC2 + 8u * N);
+                WG_T(2);
             } else if (prox >= 0) {
                 // ================= prox warps: relaxation, prox, dual ascent of block k behind the forward sweep
                 struct In { double x[3], z[3], u[3], pr[8]; int type; };
-                // block `slot` (compact index) with x at xa; ds = z+ - z goes to da
-                auto load_block = [&](int slot, uint32_t xa, In &in) {
+                // block `slot` (compact index): everything that does not depend on the chain (parameters, type, z, u) is
+                // loaded BEFORE the wait on the chain's barrier, x = a_k (at xa) after it; ds = z+ - z goes to da
+                auto load_own = [&](int slot, In &in) {
                     const uint32_t pa = par_s + (uint32_t)slot * 64u, o = (uint32_t)(3 * slot) * 8u;
                     wg_ld2(pa, in.pr[0], in.pr[1]); wg_ld2(pa + 16, in.pr[2], in.pr[3]);
                     wg_ld2(pa + 32, in.pr[4], in.pr[5]); wg_ld2(pa + 48, in.pr[6], in.pr[7]);
                     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(in.type) : "r"(typ_s + 4u * slot) : "memory");
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
-                        in.x[e] = wg_ld(xa + 8u * e);
                         in.z[e] = wg_ld(zs + o + 8u * e);
                         in.u[e] = wg_ld(us + o + 8u * e);
                     }
                 };
-                auto update_block = [&](int slot, uint32_t da, const In &in) {
+                auto update_block = [&](int slot, uint32_t xa, uint32_t da, In &in) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) in.x[e] = wg_ld(xa + 8u * e);
                     double v[3], zn[3];
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
@@ -435,71 +497,127 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                         if (run) { wg_st(zs + o + 8u * e, zn[e]); wg_st(us + o + 8u * e, v[e] - zn[e]); }
                     }
                 };
-                // control block k has compact index k (fast pattern); its x = a_k is at g rows 6k..6k+2, ds goes to 6k+3..
-                for (int k = prox; k < N; k += WG_PROX) {
+                // Blocks 0 .. N+1 go round the prox warps: control block k (compact index k in the fast pattern; x = a_k at g
+                // rows 6k..6k+2, ds to 6k+3..), then the two terminal blocks (x = s_N).  After each block the warp publishes
+                // its running count (release), which is what the norm warp polls.
+                for (int k = prox; k < N + 2; k += WG_PROX) {
                     In in;
-                    wg_wait(bC2 + 8u * k, ph);
-                    load_block(k, gs + (uint32_t)(6 * k) * 8u, in);
-                    update_block(k, gs + (uint32_t)(6 * k + 3) * 8u, in);
-                    wg_arrive(bP3 + 8u * k);
-                }
-                if (prox < 2) {                              // the two terminal blocks: x = s_N
-                    const int de = prox == 0 ? de_t0 : de_t1;
-                    wg_wait(bC2 + 8u * N, ph);
-                    if ((de & 0xff) != BLK_NONE) {
-                        In in;
-                        load_block(de >> 8, gN + (uint32_t)(3 * prox) * 8u, in);
-                        update_block(de >> 8, gN + (uint32_t)(6 + 3 * prox) * 8u, in);
+                    if (k < N) {
+                        load_own(k, in);
+                        wg_wait_spin(bC2 + 8u * k, ph);
+                        update_block(k, gs + (uint32_t)(6 * k) * 8u, gs + (uint32_t)(6 * k + 3) * 8u, in);
+                    } else {
+                        const int tb = k - N;
+                        const int de = tb == 0 ? de_t0 : de_t1;
+                        if ((de & 0xff) != BLK_NONE) load_own(de >> 8, in);
+                        wg_wait_spin(bC2 + 8u * N, ph);
+                        if ((de & 0xff) != BLK_NONE)
+                            update_block(de >> 8, gN + (uint32_t)(3 * tb) * 8u, gN + (uint32_t)(6 + 3 * tb) * 8u, in);
                     }
-                    wg_arrive(bP3 + 8u * N);
+                    ++pcount;
+                    __syncwarp();
+                    if ((tid & 31) == 0)
+                        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(prog_s + 4u * prox), "r"(pcount) : "memory");
+                    WG_TK(1, k);
                 }
+                WG_T(3);
             } else if (norms) {
                 // ================= the five norm accumulators, blocks in the oracle's order, behind the prox warps
                 double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
-                auto add_block = [&](uint32_t xa, uint32_t za, uint32_t ua, uint32_t da) {
-                    double x[3], z[3], u[3], dd[3];
+                struct In { double x[3], z[3], u[3], dd[3]; };
+                auto load_block = [&](uint32_t xa, uint32_t za, uint32_t ua, uint32_t da, In &in) {
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
-                        x[e] = wg_ld(xa + 8u * e); z[e] = wg_ld(za + 8u * e);
-                        u[e] = wg_ld(ua + 8u * e); dd[e] = wg_ld(da + 8u * e);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        const double dr = x[e] - z[e];
-                        rr = fma(dr, dr, rr);
-                        ss = fma(dd[e], dd[e], ss);
-                        xx = fma(x[e], x[e], xx);
-                        zz = fma(z[e], z[e], zz);
-                        uu = fma(u[e], u[e], uu);
+                        in.x[e] = wg_ld(xa + 8u * e); in.z[e] = wg_ld(za + 8u * e);
+                        in.u[e] = wg_ld(ua + 8u * e); in.dd[e] = wg_ld(da + 8u * e);
                     }
                 };
-                for (int k = 0; k < N; ++k) {
-                    wg_wait(bP3 + 8u * k, ph);
-                    add_block(gs + (uint32_t)(6 * k) * 8u, zs + (uint32_t)(3 * k) * 8u, us + (uint32_t)(3 * k) * 8u,
-                              gs + (uint32_t)(6 * k + 3) * 8u);
+                auto add_block = [&](const In &in) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const double dr = in.x[e] - in.z[e];
+                        rr = fma(dr, dr, rr);
+                        ss = fma(in.dd[e], in.dd[e], ss);
+                        xx = fma(in.x[e], in.x[e], xx);
+                        zz = fma(in.z[e], in.z[e], zz);
+                        uu = fma(in.u[e], in.u[e], uu);
+                    }
+                };
+                // `ready` = number of leading blocks known to be finished, from the prox warps' counters: warp w has done
+                // its first c_w blocks of this iteration, i.e. every block below 4 c_w + w of its residue class
+                int ready = 0;
+                auto need = [&](int k) {
+                    int spins = 0;
+                    while (ready <= k) {
+                        uint32_t c[WG_PROX];
+#pragma unroll
+                        for (int w = 0; w < WG_PROX; ++w)
+                            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(c[w]) : "r"(prog_s + 4u * w) : "memory");
+                        int r = 1 << 30;
+#pragma unroll
+                        for (int w = 0; w < WG_PROX; ++w) r = min(r, 4 * (int)(c[w] - nbase[w]) + w);
+                        ready = r;
+                        if (++spins > (1 << 22)) __trap();
+                    }
+                };
+                // Runs of finished blocks: one poll tells how far the prox warps have got, then blocks k .. kend-1 go through
+                // a branch-free, software-pipelined loop (block k + 1 is loaded before block k is accumulated).  A lone warp
+                // pays 10-15 cycles for every taken branch, so nothing is tested per block.
+                {
+                    auto load_k = [&](int k, In &in) {
+                        load_block(gs + (uint32_t)(6 * k) * 8u, zs + (uint32_t)(3 * k) * 8u, us + (uint32_t)(3 * k) * 8u,
+                                   gs + (uint32_t)(6 * k + 3) * 8u, in);
+                    };
+                    int k = 0;
+                    while (k < N) {
+                        need(k);
+                        const int kend = min(ready, N);
+                        In a, b;
+                        load_k(k, a);
+                        for (; k + 2 < kend; k += 2) {
+                            load_k(k + 1, b);
+                            add_block(a);
+                            load_k(k + 2, a);
+                            add_block(b);
+                        }
+                        if (k + 1 < kend) { load_k(k + 1, b); add_block(a); add_block(b); k += 2; }
+                        else { add_block(a); k += 1; }
+                        WG_TK(2, k - 1);
+                    }
                 }
-                wg_wait(bP3 + 8u * N, ph);
+                WG_T(4);
+                need(N + 1);
 #pragma unroll
                 for (int tb = 0; tb < 2; ++tb) {
                     const int de = tb == 0 ? de_t0 : de_t1;
                     if ((de & 0xff) == BLK_NONE) continue;
                     const uint32_t o = (uint32_t)(3 * (de >> 8)) * 8u;
-                    add_block(gN + (uint32_t)(3 * tb) * 8u, zs + o, us + o, gN + (uint32_t)(6 + 3 * tb) * 8u);
+                    In in;
+                    load_block(gN + (uint32_t)(3 * tb) * 8u, zs + o, us + o, gN + (uint32_t)(6 + 3 * tb) * 8u, in);
+                    add_block(in);
                 }
+#pragma unroll
+                for (int w = 0; w < WG_PROX; ++w) nbase[w] += (uint32_t)((N + 2 - w + WG_PROX - 1) / WG_PROX);
                 wg_st(nrs, rr); wg_st(nrs + 8, ss); wg_st(nrs + 16, xx); wg_st(nrs + 24, zz); wg_st(nrs + 32, uu);
             }
+            WG_T(5);
             ph ^= 1u;
             __syncthreads();
+            WG_T(6);
 
-            // ================= stopping test and rho update: every warp, for its own copy of the lane's state
+            // ================= stopping test and rho update: every warp, for its own copy of the lane's state.  The five
+            // square roots are the long part (dependent Newton chains, ~150 cycles each): warps 0-4 take one each
+            if (warp < 5) wg_st(nrs0 + 80u + 8u * warp, sqrt(wg_ld(nrs + 8u * warp)));
+            __syncthreads();
             if (run) {
                 ++it;
                 sigma = 1.0;
-                r_norm = sqrt(wg_ld(nrs));
-                s_norm = rho * sqrt(wg_ld(nrs + 8));
-                const double nx = sqrt(wg_ld(nrs + 16)), nz = sqrt(wg_ld(nrs + 24));
+                const uint32_t rts = nrs0 + 80u;
+                r_norm = wg_ld(rts);
+                s_norm = rho * wg_ld(rts + 8);
+                const double nx = wg_ld(rts + 16), nz = wg_ld(rts + 24);
                 eps_pri = fma(P.reltol, nx > nz ? nx : nz, P.sqrtn_abs);
-                eps_dual = fma(P.reltol, rho * sqrt(wg_ld(nrs + 32)), P.sqrtn_abs);
+                eps_dual = fma(P.reltol, rho * wg_ld(rts + 32), P.sqrtn_abs);
                 if (P.hist && warp == 4) {
                     const size_t h = (size_t)(it - 1) * P.hist_ld + (P.orig ? (size_t)P.orig[p] : p);   // home column
                     P.hist[h] = r_norm;
@@ -522,8 +640,20 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     if (it >= P.max_iter) st = ST_MAX_ITER;
                 }
             }
+            WG_T(7);
         }
 
+#ifdef WG_TIMING
+        if (blockIdx.x == 0 && tid == 0) {
+            const char *names[8] = {"start", "bwd_done", "fwd_done", "prox_done", "norm_ctl", "role_done", "barrier", "stop_done"};
+            for (int w = 0; w < WG_WARPS; ++w)
+                for (int i = 0; i < 8; ++i)
+                    if (wg_tlog[w][i]) printf("wgt warp %d %-10s %lld\n", w, names[i], wg_tlog[w][i] - wg_tlog[0][0]);
+            for (int k = 0; k < 64 && k < N + 2; ++k)
+                printf("wgk %d a_pub %lld prox %lld norm %lld\n", k, wg_klog[0][k] - wg_tlog[0][0], wg_klog[1][k] - wg_tlog[0][0],
+                       wg_klog[2][k] - wg_tlog[0][0]);
+        }
+#endif
         // ---- tile out (the loop ends behind a barrier or before any phase of a new iteration has started)
         __syncthreads();
         if (valid) {

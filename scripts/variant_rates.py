@@ -13,6 +13,8 @@ chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 widths = [int(w) for w in (sys.argv[4] if len(sys.argv) > 4 else "1024,4096,8192,16384,65536").split(",")]
 variants = (sys.argv[5] if len(sys.argv) > 5 else "thread_wide,thread2,tile,wg").split(",")
 pkg = graft.load_pkg()
+if os.environ.get("ADMMB_LIB"):          # developer build of the library (e.g. -DWG_TIMING in lib_timing/)
+    pkg._lib.LIB_PATH = os.path.abspath(os.environ["ADMMB_LIB"])
 P = pkg.problems
 gen = {"cfg2": P.cfg2_cw_batch, "cfg3": P.cfg3_lowthrust_soc, "cfg5": P.cfg5_montecarlo}[name]
 for w in widths:
