@@ -316,17 +316,25 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     uploaded = true;
 }
 
+// Widest working set the warp-group kernel takes when the choice is the library's.  Measured on B200 (cfg2, N = 50,
+// scripts/variant_rates.py): the warp-group kernel runs 4.1e8 problem-iterations/s at any width >= 4,096 and 10 us per
+// iteration below; one problem per thread needs 32 us per iteration up to 16,384 problems (2.6e8 at 8,192, 4.8e8 at
+// 16,384), so the two cross between 12 k and 14 k problems.  (Tuning knob; it has no effect on results.)
+static int64_t wg_max_width()
+{
+    static const int64_t w = getenv("ADMMB_WG_WIDTH") ? atoll(getenv("ADMMB_WG_WIDTH")) : 12288;
+    return w;
+}
+
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
     static const bool p2_default = getenv("ADMMB_P2") ? atoi(getenv("ADMMB_P2")) != 0 : true;
-    // widest working set the resident-tile kernel takes when the choice is the library's (tuning knob; no effect on results)
-    static const int64_t tile_width = getenv("ADMMB_TILE_WIDTH") ? atoll(getenv("ADMMB_TILE_WIDTH")) : 16384;
     IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default, kernel_variant,
                     rows_zu, device, time_invariant};
     last_kernel = KV_THREAD;
     if (FSH && FSMEM) {
-        const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && P.n_active <= tile_width);
+        const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && P.n_active <= wg_max_width());
         const bool tile = kernel_variant == KV_TILE;
         if (wg && launch_iterate_wg(c, P, adapt)) last_kernel = KV_WG;
         else if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
@@ -522,6 +530,12 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         // below this many running problems one warp's serial sweep bounds the Riccati kernel (~33 us per iteration)
         // and the GEMM + prox pair is faster (32 us at 8,192, 21 us at 1,024: DESIGN 6.3)
         const int64_t tail_width = getenv("ADMMB_TF32_SWITCH") ? atoll(getenv("ADMMB_TF32_SWITCH")) : 8192;
+        int wg_tile = 0;
+        {
+            IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, false, kernel_variant,
+                            rows_zu, device, time_invariant};
+            if (shared_factor && fsmem) wg_tile = iterate_wg_tile_width(c);
+        }
         int done_iters = 0;
         while (width > 0 && done_iters < op->max_iter && !(tf32_tail && width <= tail_width)) {
             P.chunk = chunk;
@@ -561,15 +575,26 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             int cnt[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt, split_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
-            if (op->chunk <= 0) {
+            // The warp-group kernel holds a whole tile of problems per CTA for the launch: finished problems idle in their
+            // lanes at no cost to the others, and a launch's time only depends on the number of PASSES (tiles per CTA).  So
+            // the working set is repacked only when that drops a pass, and a single-pass working set runs in long launches
+            // (a CTA leaves as soon as all its problems are done).
+            bool wg_skip = false;
+            if (last_kernel == KV_WG && wg_tile > 0 && cnt[0] > 0 && kernel_variant == KV_AUTO) {
+                auto passes = [&](int64_t w) { const int64_t tiles = (w + wg_tile - 1) / wg_tile; return (tiles + num_sms - 1) / num_sms; };
+                const int64_t now = passes(width), then = passes((int64_t)round_up((size_t)cnt[0], 32));
+                wg_skip = then >= now;
+                if (op->chunk <= 0) chunk = now <= 1 ? 1000 : 200;
+            } else if (op->chunk <= 0) {
                 // adapt the launch length: finished problems idle until the launch ends, so aim at <= 1 % of the
                 // working set finishing per launch, estimated from the finish rate of the launch just done
                 const int prev = chunk;
                 if (cnt[1] == 0) chunk = std::min(chunk * 2, chunk_max);
                 else chunk = (int)std::min<long long>(chunk_max, std::max<long long>(50, (long long)width * prev / (100LL * cnt[1])));
-                if (adapt && P.every > 0 && chunk > P.every) chunk = (chunk / P.every) * P.every;
             }
+            if (adapt && P.every > 0 && chunk > P.every) chunk = (chunk / P.every) * P.every;
             if (cnt[0] == (int)width) continue;                 // nobody finished in this launch
+            if (wg_skip) continue;                              // warp-group kernel: no pass to gain from a repack
             if (no_repack && cnt[0] > 0 && cur_set < 0) continue;   // debug: finished lanes just idle
             repack(cnt[0], cnt[1]);
             if (tf32_tail && width > 0 && width <= tail_width) break;

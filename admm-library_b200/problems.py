@@ -242,12 +242,15 @@ def cfg2_cw_batch(batch: int = 4096, N: int = 50, seed: int = 2, dv_max: float =
     bt, bp = make_blocks(N, BLK_L1_BOX, lam=1.0, lo=-dv_max, hi=dv_max, terminal=np.zeros(6))
     prob = dict(N=N, A=A, B=B, c=None, Q=None, R=None, q=None,
                 s0=_dispersed_s0(batch, seed, spread), block_type=bt, block_par=bp)
-    opts = dict(DEFAULT_OPTS, rho=1.0, alpha=1.0, max_iter=20000)
+    # rho and alpha tuned once with the oracle (round 2: 1,024 problems, rho in 1 .. 300, alpha in 1.0 .. 1.8) and frozen:
+    # every problem converges to 1e-6 in 2,000 .. 20,000 iterations (median 8,300); with round 1's rho = 1 one problem in
+    # eight was still running at 20,000.  Over-relaxation does not help these LP-like problems.
+    opts = dict(DEFAULT_OPTS, rho=40.0, alpha=1.0, max_iter=40000)
     return prob, opts
 
 
 def cfg3_lowthrust_soc(batch: int = 65536, N: int = 100, seed: int = 3,
-                       a_max: float = 1.5) -> tuple[dict, dict]:
+                       a_max: float = 2.5) -> tuple[dict, dict]:
     """configs[2]: CW ZOH low-thrust transfers, thrust-magnitude SOC (l2 + ball) on each control."""
     T = 2.0 * np.pi / N
     Phi, Gam = cw_zoh(T)
@@ -256,15 +259,20 @@ def cfg3_lowthrust_soc(batch: int = 65536, N: int = 100, seed: int = 3,
     bt, bp = make_blocks(N, BLK_L2_BALL, lam=T, rad=a_max, terminal=np.zeros(6))
     prob = dict(N=N, A=A, B=B, c=None, Q=None, R=None, q=None,
                 s0=_dispersed_s0(batch, seed), block_type=bt, block_par=bp)
-    opts = dict(DEFAULT_OPTS, rho=0.1, alpha=1.0, max_iter=20000)
+    # a_max = 2.5: with round 1's 1.5 one dispersed start in ten could not reach the target within the horizon at all
+    # (thrust saturated on every stage, primal residual stuck).  rho, alpha tuned once with the oracle: every problem
+    # converges in 800 .. 4,000 iterations (median 1,400).
+    opts = dict(DEFAULT_OPTS, rho=0.1, alpha=1.6, max_iter=20000)
     return prob, opts
 
 
 def cfg4_elliptic(batch: int = 16384, N: int = 50, seed: int = 4,
-                  a_max: float = 3.0) -> tuple[dict, dict]:
-    """configs[3]: elliptic-orbit rendezvous with per-problem time-varying STMs (Riccati path)."""
+                  a_max: float = 10.0, e_max: float = 0.5) -> tuple[dict, dict]:
+    """configs[3]: elliptic-orbit rendezvous with per-problem time-varying STMs (Riccati path).
+    e ~ U(0.05, 0.5), a_max = 10: with round 1's e up to 0.7 and a_max = 3 a quarter of the problems were infeasible
+    (thrust saturated on every stage).  rho, alpha tuned once with the oracle: all converge, median 1,700 iterations."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    e = rng.uniform(0.05, 0.7, batch)
+    e = rng.uniform(0.05, e_max, batch)
     th0 = rng.uniform(0.0, 2.0 * np.pi, batch)
     T = 2.0 * np.pi / N
     A, B = elliptic_stage_matrices(e, th0, N, T)
@@ -272,15 +280,18 @@ def cfg4_elliptic(batch: int = 16384, N: int = 50, seed: int = 4,
     s0 = S0_NOMINAL[None, :] + S0_SIGMA[None, :] * rng.standard_normal((batch, 6))
     prob = dict(N=N, A=A, B=B, c=None, Q=None, R=None, q=None,
                 s0=s0, block_type=bt, block_par=bp, meta=dict(e=e, theta0=th0))
-    opts = dict(DEFAULT_OPTS, rho=0.1, alpha=1.0, max_iter=20000)
+    opts = dict(DEFAULT_OPTS, rho=0.05, alpha=1.6, max_iter=40000)
     return prob, opts
 
 
 def cfg5_montecarlo(batch: int = 1048576, N: int = 50, seed: int = 5,
-                    dv_max: float = 0.4) -> tuple[dict, dict]:
-    """configs[4]: Monte Carlo dispersion sweep, 10x spread, adaptive rho + per-problem early exit."""
-    prob, opts = cfg2_cw_batch(batch, N, seed, dv_max, spread=10.0)
-    opts = dict(opts, adapt_rho=1, adapt_mu=10.0, adapt_tau=2.0, adapt_every=25, adapt_until=1000)
+                    dv_max: float = 1.0, spread: float = 5.0) -> tuple[dict, dict]:
+    """configs[4]: Monte Carlo dispersion sweep (5x the dispersion of config 2, so iteration counts vary by more than
+    10x), adaptive rho + per-problem early exit.  Residual balancing with the textbook mu = 10 drives rho of these
+    LP-like problems to ~1, where they converge 2-3x slower than at rho = 40 (measured with the oracle, round 2), so
+    the trigger only corrects gross imbalance (mu = 1000) during the first 1000 iterations."""
+    prob, opts = cfg2_cw_batch(batch, N, seed, dv_max, spread=spread)
+    opts = dict(opts, adapt_rho=1, adapt_mu=1000.0, adapt_tau=2.0, adapt_every=100, adapt_until=1000, max_iter=60000)
     return prob, opts
 
 
