@@ -435,6 +435,9 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     CK(cudaEventRecord(ev0, stream));
     CK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 4, stream));
     CK(cudaMemsetAsync(fac_status.p, 0, sizeof(int) * ld, stream));
+    // history entries of iterations a problem never runs are NaN (all-ones bit pattern), as in the oracle: callers of
+    // the C ABI and the MEX gateway get them as they are
+    if (op->history && hist_alloc) CK(cudaMemsetAsync(hist.p, 0xFF, sizeof(double) * 5 * (size_t)max_iter_alloc * ld, stream));
 
     // ---- factorisation (row a1), once per rho
     if (shared_factor) {
@@ -529,7 +532,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         const int chunk_max = op->chunk > 0 ? op->chunk : 400;
         // below this many running problems one warp's serial sweep bounds the Riccati kernel (~33 us per iteration)
         // and the GEMM + prox pair is faster (32 us at 8,192, 21 us at 1,024: DESIGN 6.3)
-        const int64_t tail_width = getenv("ADMMB_TF32_SWITCH") ? atoll(getenv("ADMMB_TF32_SWITCH")) : 8192;
+        const int64_t tail_width = op->tf32_switch > 0 ? op->tf32_switch : (op->tf32_switch < 0 ? 0 : 8192);   // opts.tf32_switch
         int wg_tile = 0;
         {
             IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, false, kernel_variant,
@@ -692,6 +695,8 @@ struct admmb_ctx {
     bool uploaded = false;
     int64_t batch = 0;
     int max_iter = 0;
+    admmb_opts up_opts;          // the options of the last successful admmb_upload: they fixed the structural choices
+                                 // (shared factor or not, dense / tensor-core state, history buffers) that a run must keep
 };
 
 namespace {
@@ -715,6 +720,8 @@ int cuda_code(cudaError_t e)
     return ADMMB_E_CUDA;
 }
 
+int validate_opts(admmb_ctx *h, const admmb_opts *op);
+
 int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
 {
     if (!pb || !op) return fail(h, ADMMB_E_BADARG, "null problem/opts");
@@ -733,6 +740,22 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
     for (int k = 0; k < pb->N; ++k)
         if (pb->block_type[3 * k + 2] == ADMMB_BLK_NONE && !pb->R)
             return fail(h, ADMMB_E_BADARG, "control block %d is unsplit and R is absent: x-update is singular", k);
+    if (op->xupdate == ADMMB_XUPDATE_DENSE) {
+        const bool has_P = pb->Q || pb->R;
+        if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
+        if (has_P && (op->adapt_rho || pb->rho0)) return fail(h, ADMMB_E_BADARG, "dense x-update with P != 0 needs one shared rho");
+        if (op->history) return fail(h, ADMMB_E_BADARG, "history is not recorded on the dense path");
+        if (op->adapt_rho) return fail(h, ADMMB_E_BADARG, "adaptive rho is not implemented on the dense path (use xupdate = auto / riccati)");
+    }
+    if (8 * (size_t)nb * sizeof(double) + 4 * (size_t)nb + 4096 > 200 * 1024)
+        return fail(h, ADMMB_E_BADARG, "N = %d: the block parameter table (%zu KB) does not fit the shared memory the iteration "
+                                       "kernels stage it in (N <= 1000)", pb->N, 8 * (size_t)nb * sizeof(double) / 1024);
+    return validate_opts(h, op);
+}
+
+// the part of the checks that concerns the options alone (also applied to the options of admmb_run)
+int validate_opts(admmb_ctx *h, const admmb_opts *op)
+{
     if (!(op->rho > 0.0) || !std::isfinite(op->rho)) return fail(h, ADMMB_E_BADARG, "rho must be > 0");
     if (!(op->alpha > 0.0 && op->alpha < 2.0)) return fail(h, ADMMB_E_BADARG, "alpha must be in (0,2)");
     if (!(op->abstol >= 0.0) || !(op->reltol >= 0.0)) return fail(h, ADMMB_E_BADARG, "tolerances must be >= 0");
@@ -746,13 +769,6 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
     // (narrow working sets, eligible problems; otherwise the FP64 Riccati kernel runs)
     if (op->precision == ADMMB_PREC_TF32 && op->xupdate == ADMMB_XUPDATE_RICCATI)
         return fail(h, ADMMB_E_BADARG, "TF32 does not apply to xupdate = riccati (use dense or auto)");
-    if (op->xupdate == ADMMB_XUPDATE_DENSE) {
-        const bool has_P = pb->Q || pb->R;
-        if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
-        if (has_P && (op->adapt_rho || pb->rho0)) return fail(h, ADMMB_E_BADARG, "dense x-update with P != 0 needs one shared rho");
-        if (op->history) return fail(h, ADMMB_E_BADARG, "history is not recorded on the dense path");
-        if (op->adapt_rho) return fail(h, ADMMB_E_BADARG, "adaptive rho is not implemented on the dense path (use xupdate = auto / riccati)");
-    }
     return ADMMB_OK;
 }
 
@@ -873,7 +889,7 @@ int admmb_upload(admmb_handle h, const admmb_problem *pb, const admmb_opts *op)
         });
         return (int)ADMMB_OK;
     });
-    if (rc == ADMMB_OK) { h->uploaded = true; h->batch = pb->batch; h->max_iter = op->max_iter; }
+    if (rc == ADMMB_OK) { h->uploaded = true; h->batch = pb->batch; h->max_iter = op->max_iter; h->up_opts = *op; }
     return rc;
 }
 
@@ -882,7 +898,23 @@ int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
     if (!h || !op) return ADMMB_E_BADARG;
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->uploaded) return fail(h, ADMMB_E_STATE, "admmb_run called before a successful admmb_upload");
-    if (op->max_iter != h->max_iter && op->history) return fail(h, ADMMB_E_BADARG, "max_iter differs from the uploaded one while history is on");
+    // rho, alpha, the tolerances, chunk, kernel and the adaptation parameters may change between runs of one upload; what
+    // upload built its device state on may not (a shared factor computed for ONE rho, dense / tensor-core operands,
+    // the size of the history buffers)
+    {
+        int rc0 = validate_opts(h, op);
+        if (rc0 != ADMMB_OK) return rc0;
+        const admmb_opts &u0 = h->up_opts;
+        if ((op->adapt_rho != 0) != (u0.adapt_rho != 0) || op->xupdate != u0.xupdate || op->precision != u0.precision ||
+            (op->history != 0) != (u0.history != 0))
+            return fail(h, ADMMB_E_BADARG, "adapt_rho, xupdate, precision and history must be the ones given to admmb_upload "
+                                           "(upload the problem again to change them)");
+        if (op->history && op->max_iter != u0.max_iter)
+            return fail(h, ADMMB_E_BADARG, "max_iter differs from the uploaded one while history is on");
+        const Shard &s0 = h->shards[0];
+        if ((s0.use_dense || s0.tf32_tail) && (s0.has_Q || s0.has_R) && op->rho != u0.rho)
+            return fail(h, ADMMB_E_BADARG, "the dense factor was built for the rho given to admmb_upload (P != 0): upload again to change rho");
+    }
     std::vector<admmb_result> part(h->shards.size());
     int rc = guarded(h, [&]() {
         for_each_shard(h, [&](int g) {

@@ -186,7 +186,7 @@ void condensed_loop(Shard &s, const admmb_opts *op, int split, int it0, bool tai
     auto since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
-    const int refresh = getenv("ADMMB_TF32_REFRESH") ? atoi(getenv("ADMMB_TF32_REFRESH")) : 1000;
+    const int refresh = op->tf32_refresh > 0 ? op->tf32_refresh : (op->tf32_refresh < 0 ? 0 : 1000);      // opts.tf32_refresh
     const int zu_compact = tail ? 1 : 0;
     // the tail starts with a "refresh": x_R = exact x-update of the (z, u) the Riccati loop left, increment = 0
     // refresh schedule: early and often while the steps are large (that is where the increments' rounding accumulates:

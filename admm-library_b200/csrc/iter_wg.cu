@@ -30,7 +30,8 @@ void wg_set_attr(K kern, size_t smem, int device)
 int iterate_wg_tile_width(const IterLaunchCtx &c)
 {
     if (!c.fast_pattern || !c.decoupled || c.has_c || c.has_q || c.par_batched || c.rows_zu <= 0) return 0;
-    for (int tw = 32; tw >= WG_MIN_TW; --tw)
+    static const int tw_cap = getenv("ADMMB_WG_TW") ? atoi(getenv("ADMMB_WG_TW")) : 32;      // developer knob
+    for (int tw = tw_cap < 32 ? tw_cap : 32; tw >= WG_MIN_TW; --tw)
         if (wg_layout(c.N, c.rows_zu, tw).total <= WG_SMEM_MAX) return tw;
     return 0;
 }

@@ -556,7 +556,10 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                         int r = 1 << 30;
 #pragma unroll
                         for (int w = 0; w < WG_PROX; ++w) r = min(r, 4 * (int)(c[w] - nbase[w]) + w);
-                        ready = r;
+                        // warp-uniform run boundaries: loads of a counter that is bumped meanwhile can return different
+                        // values to different lanes (a wide load is served a quarter-warp at a time), and lanes beyond the
+                        // tile width are copies of its last lane that must stay in lockstep with it
+                        ready = __shfl_sync(0xffffffffu, r, 0);
                         if (++spins > (1 << 22)) __trap();
                     }
                 };

@@ -146,6 +146,7 @@ class Solver:
             msg = self._L.admmb_last_error(None)
             raise L.AdmmError(rc, msg.decode() if msg else "")
         self._keep = None
+        self._up = None
         self._n = self._batch = 0
 
     def close(self):
@@ -197,11 +198,13 @@ class Solver:
         pb = make_problem(m)
         op = make_opts(opts)
         self._check(self._L.admmb_upload(self._h, C.byref(pb), C.byref(op)))
+        self._up = (int(op.max_iter), bool(op.history))     # what the library sized its history buffers with
 
     def upload_c(self, pb: L.Problem, op: L.Opts, batch: int, n: int):
         """Upload from caller-built ctypes structs (e.g. pointing into pinned memory)."""
         self._n, self._batch = n, batch
         self._check(self._L.admmb_upload(self._h, C.byref(pb), C.byref(op)))
+        self._up = (int(op.max_iter), bool(op.history))
 
     def run(self, opts: dict | L.Opts) -> dict:
         op = opts if isinstance(opts, L.Opts) else make_opts(opts)
@@ -210,9 +213,10 @@ class Solver:
         return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches),
                     kernel_ms=r.kernel_ms, kernel_launches=int(r.kernel_launches))
 
-    def download(self, opts: dict, want=("x", "z", "u")):
-        op = make_opts(opts)
-        res = ResultBuffers(max(self._batch, 1), max(self._n, 1), op.max_iter, bool(op.history), want)
+    def download(self, opts: dict | None = None, want=("x", "z", "u")):
+        # the history buffers are sized by the UPLOADED options (the library writes max_iter_uploaded x batch values)
+        max_iter, history = getattr(self, "_up", None) or (make_opts(opts).max_iter, bool(make_opts(opts).history))
+        res = ResultBuffers(max(self._batch, 1), max(self._n, 1), max_iter, history, want)
         self._check(self._L.admmb_download(self._h, C.byref(res.c)))
         return res.x, res.z, res.u, res.hist_dict()
 

@@ -300,3 +300,34 @@ def test_long_horizon_factor_read_from_global(solver, cpu_oracle, P, coupled):
         prob = dict(prob, A=prob["A"] + 1e-3 * rng.standard_normal(prob["A"].shape))
     got, ref = _both(solver, cpu_oracle, prob, dict(opts, max_iter=25, rho=1.0))
     assert_bit_identical(got, ref, f"N=300 coupled={coupled}")
+
+
+# ---- benchmark-sized batches: the kernels a 65,536-problem solve goes through -- two problems per
+# thread at full width, the uncapped one-problem build once the working set fits one wave, the warp-group kernel below
+# 12,288 running problems, repacks in between -- held against the oracle on three 256-problem slices (first, middle and
+# last columns of the shard).  Only the automatic choice is meaningful here, so the pinned variants are skipped.
+def _slices_vs_oracle(solver, cpu_oracle, prob, opts, what):
+    x, z, u, h = solver.solve(prob, opts)
+    B = prob["s0"].shape[0]
+    idx = np.concatenate([np.arange(0, 256), np.arange(B // 2 - 128, B // 2 + 128), np.arange(B - 256, B)])
+    sub = dict(prob, s0=np.ascontiguousarray(prob["s0"][idx]))        # shared model: only the initial states are per problem
+    ref = cpu_oracle.solve(sub, opts)
+    got = (x[idx], z[idx], u[idx], {k: (v[idx] if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v)
+                                     for k, v in h.items() if k != "hist"})
+    assert_bit_identical(got, ref, what)
+    return h
+
+
+def test_full_width_65536_fixed_iterations(solver, cpu_oracle, P, kernel_variant):
+    if kernel_variant != "auto":
+        pytest.skip("benchmark-sized batch: the automatic kernel choice is what is under test")
+    prob, opts = P.cfg2_cw_batch(batch=65536, N=50, seed=1002)
+    _slices_vs_oracle(solver, cpu_oracle, prob, dict(opts, max_iter=300), "65,536 x N=50, 300 iterations")
+
+
+def test_full_width_65536_to_tolerance(solver, cpu_oracle, P, kernel_variant):
+    if kernel_variant != "auto":
+        pytest.skip("benchmark-sized batch: the automatic kernel choice is what is under test")
+    prob, opts = P.cfg2_cw_batch(batch=65536, N=50, seed=1002)
+    h = _slices_vs_oracle(solver, cpu_oracle, prob, opts, "65,536 x N=50, to tolerance")
+    assert (h["status"] == 0).mean() > 0.999

@@ -311,12 +311,14 @@ def test_tf32_incremental_reaches_fp64_tolerance(solver, cpu_oracle, P):
     assert opts["abstol"] <= 1e-6 and opts["reltol"] <= 1e-6
     xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
     x, z, u, h = solver.solve(prob, dict(opts, xupdate="dense", precision="tf32"))
-    # (some of these problems do not reach 1e-6 within max_iter in FP64 either: compare the converged sets)
-    assert (hr["status"] == 0).mean() > 0.7
-    assert (h["status"] == hr["status"]).mean() > 0.99
+    # every problem of the (re-tuned, round 2) workload converges in FP64; the TF32 class must converge on the same set,
+    # in nearly the same number of iterations in the median (single problems stop up to ~30 % earlier or later: the
+    # stopping test of a slowly converging LP is crossed at a shallow angle)
+    assert (hr["status"] == 0).all()
+    assert (h["status"] == hr["status"]).all()
     both = (h["status"] == 0) & (hr["status"] == 0)
     ratio = h["iters"][both].astype(float) / hr["iters"][both]
-    assert 0.98 < np.median(ratio) < 1.02 and 0.8 < ratio.min() and ratio.max() < 1.25
+    assert 0.98 < np.median(ratio) < 1.02 and 0.6 < ratio.min() and ratio.max() < 1.6
     sx = np.abs(xr).max()
     # these fuel-optimal (L1) problems are nearly degenerate: points that satisfy the 1e-6 stopping test are much farther
     # than 1e-6 apart along flat directions (the FP64 oracle's own x still moves by ~2e-4 |x| when its tolerance is
@@ -333,6 +335,25 @@ def test_tf32_incremental_reaches_fp64_tolerance(solver, cpu_oracle, P):
     s_next = np.concatenate([s[:, 1:], x[:, 9 * N:].reshape(-1, 1, 6)], axis=1)
     res = s_next - np.einsum("kij,pkj->pki", A, s) - np.einsum("kij,pkj->pki", B, a)
     assert np.abs(res).max() <= 1e-12 * sx
+
+
+@pytest.mark.gpu
+def test_tf32_converged_point_within_1e4_of_fp64(solver, cpu_oracle, P):
+    """north_star: "final x/z/u within ... 1e-4 where TF32 is used, stated".  Both sides are solved far beyond the working
+    tolerance (1e-9), so that the comparison is between converged POINTS and not between two places on the flat bottom
+    of a nearly degenerate LP at which a 1e-6 stopping test happens to fire: equal converged sets and
+    max |x - x_ref|, |z - z_ref| <= 1e-4 |x|."""
+    prob, opts = P.cfg2_cw_batch(batch=256, N=50, seed=12)
+    o = dict(opts, abstol=1e-9, reltol=1e-9, max_iter=150000)
+    xr, zr, ur, hr = cpu_oracle.solve(prob, o)
+    x, z, u, h = solver.solve(prob, dict(o, xupdate="dense", precision="tf32"))
+    assert (hr["status"] == 0).mean() > 0.99
+    assert np.array_equal(h["status"], hr["status"])
+    both = (h["status"] == 0) & (hr["status"] == 0)
+    sx = np.abs(xr).max()
+    err_x, err_z = np.abs(x[both] - xr[both]).max() / sx, np.abs(z[both] - zr[both]).max() / sx
+    print(f"tf32 vs fp64 at tolerance 1e-9: max |dx| / |x| = {err_x:.2e}, max |dz| / |x| = {err_z:.2e}")
+    assert err_x <= 1e-4 and err_z <= 1e-4
 
 
 @pytest.mark.gpu
@@ -372,11 +393,7 @@ def test_tf32_auto_riccati_then_tensor_core_tail(solver, cpu_oracle, P, switch):
     prob, opts = P.cfg2_cw_batch(batch=1500, N=20, seed=31)
     opts = dict(opts, max_iter=6000, abstol=1e-6, reltol=1e-6)
     xr, zr, ur, hr = cpu_oracle.solve(prob, opts)
-    os.environ["ADMMB_TF32_SWITCH"] = str(switch)
-    try:
-        x, z, u, h = solver.solve(prob, dict(opts, precision="tf32"))
-    finally:
-        del os.environ["ADMMB_TF32_SWITCH"]
+    x, z, u, h = solver.solve(prob, dict(opts, precision="tf32", tf32_switch=switch))
     assert (hr["status"] == 0).mean() > 0.6
     assert (h["status"] == hr["status"]).mean() > 0.99
     both = (h["status"] == 0) & (hr["status"] == 0)
