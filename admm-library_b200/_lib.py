@@ -16,7 +16,7 @@ ERROR_NAMES = {E_BADARG: "ADMMB_E_BADARG", E_CUDA: "ADMMB_E_CUDA", E_NCCL: "ADMM
                E_NOMEM: "ADMMB_E_NOMEM", E_NODEVICE: "ADMMB_E_NODEVICE", E_STATE: "ADMMB_E_STATE"}
 
 EXPORTS = ["admmb_version", "admmb_create", "admmb_destroy", "admmb_last_error", "admmb_device_count",
-           "admmb_solve", "admmb_upload", "admmb_run", "admmb_download", "admmb_set_stream",
+           "admmb_solve", "admmb_upload", "admmb_run", "admmb_download", "admmb_set_stream", "admmb_shift_resolve",
            "admmb_k_riccati_factor", "admmb_k_xupdate_riccati", "admmb_k_prox_dual_residuals",
            "admmb_k_dense_factor", "admmb_k_xupdate_dense"]
 
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     L.admmb_run.argtypes = [H, C.POINTER(Opts), C.POINTER(Result)]
     L.admmb_download.argtypes = [H, C.POINTER(Result)]
     L.admmb_set_stream.argtypes = [H, C.c_void_p]
+    L.admmb_shift_resolve.argtypes = [H, C.c_int32, c_dp, C.POINTER(Opts), C.POINTER(Result)]
     L.admmb_k_riccati_factor.argtypes = [H, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, c_ip, c_dp]
     L.admmb_k_xupdate_riccati.argtypes = [H, C.c_int32, C.c_int64, c_dp, C.c_int32, c_dp, c_dp, c_dp]
     L.admmb_k_prox_dual_residuals.argtypes = [H, C.c_int32, C.c_int64, c_ip, c_dp, C.c_int32, c_dp,

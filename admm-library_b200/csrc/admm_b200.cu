@@ -181,6 +181,7 @@ struct Shard {
     void upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt);
     void run(const admmb_opts *op, admmb_result *res);
     void download(admmb_result *res);
+    void shift_warm_start(int k, const double *s0_new_host);
     template <bool FSH, bool FSMEM>
     void launch_iterate(const IterParams &P, bool adapt);
 };
@@ -404,6 +405,70 @@ void Shard::repack(int n_keep, int n_fin)
     cur_set = nxt;
     width = n_keep;
     ld_cur = ld_new;
+}
+
+// Receding-horizon warm start: split block `slot` of the next solve starts from the block `src[slot]`
+// of the solution just computed (the same block k stages later; -1: beyond the horizon, start from zero).  u is stored
+// with a pending scale after a rho change, so the scale is applied here.
+__global__ void k_shift_warm(int64_t batch, size_t ld, int nslots, const int *src, const double *z, const double *u,
+                             const double *usc, double *z0, double *u0)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    const double sc = usc[p];
+    for (int slot = blockIdx.y; slot < nslots; slot += gridDim.y) {
+        const int from = src[slot];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const size_t r = (size_t)(3 * slot + e) * ld + p;
+            z0[r] = from >= 0 ? z[(size_t)(3 * from + e) * ld + p] : 0.0;
+            u0[r] = from >= 0 ? u[(size_t)(3 * from + e) * ld + p] * sc : 0.0;
+        }
+    }
+}
+
+// The solved batch stays on the device; its (z, u), shifted by k stages, become the warm start of the next solve and the
+// initial states are replaced by s0_new (host, [6 x batch]) or, when that is null, by the solution's own state at stage k.
+void Shard::shift_warm_start(int k, const double *s0_new_host)
+{
+    CK(cudaSetDevice(device));
+    std::vector<int> src(nsplitblk, -1);
+    for (int b = 0; b < nb; ++b) {
+        if ((h_bdesc[b] & 0xff) == BLK_NONE) continue;
+        const int slot = h_bdesc[b] >> 8;
+        if (b >= 3 * N) { src[slot] = slot; continue; }          // terminal blocks keep their own iterate
+        const int from = b + 3 * k;
+        if (from < 3 * N && (h_bdesc[from] & 0xff) != BLK_NONE) src[slot] = h_bdesc[from] >> 8;
+    }
+    istage.alloc(nsplitblk);
+    CK(cudaMemcpyAsync(istage.p, src.data(), sizeof(int) * nsplitblk, cudaMemcpyHostToDevice, stream));
+    z0c.alloc((size_t)rows_zu * ld);
+    u0c.alloc((size_t)rows_zu * ld);
+    if (!s0_new_host) {
+        // the solution's state at stage k: rows 9k .. 9k+5 of x (rebuilt from d exactly as for download)
+        xo.alloc((size_t)n * ld);
+        const unsigned gb = (unsigned)((batch + 127) / 128);
+        if (shared_factor) {
+            if (has_c) k_output<true, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p, nullptr, nullptr);
+            else k_output<true, false><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p, nullptr, nullptr);
+        } else {
+            if (has_c) k_output<false, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p, nullptr, nullptr);
+            else k_output<false, false><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p, nullptr, nullptr);
+        }
+        ++launches;
+        CK(cudaGetLastError());
+    }
+    dim3 grid((unsigned)((batch + 127) / 128), (unsigned)std::min(nsplitblk, 64));
+    k_shift_warm<<<grid, 128, 0, stream>>>(batch, ld, nsplitblk, istage.p, z.p, u.p, usc.p, z0c.p, u0c.p);
+    ++launches;
+    CK(cudaGetLastError());
+    if (s0_new_host) upload_rows(s0_new_host + (size_t)p_begin * 6, batch, 6, s0.p, nullptr);
+    else
+        for (int i = 0; i < 6; ++i)
+            CK(cudaMemcpyAsync(s0.p + (size_t)i * ld, xo.p + (size_t)(9 * k + i) * ld, sizeof(double) * ld,
+                               cudaMemcpyDeviceToDevice, stream));
+    has_z0 = has_u0 = true;
+    CK(cudaStreamSynchronize(stream));       // `src` and the staging buffer are reused by the caller
 }
 
 __global__ void k_stats(int64_t batch, const int *iters, const int *status, unsigned long long *counters)
@@ -945,6 +1010,29 @@ int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
         }
     }
     return ADMMB_OK;
+}
+
+int admmb_shift_resolve(admmb_handle h, int32_t k, const double *s0_new, const admmb_opts *op, admmb_result *res)
+{
+    if (!h || !op) return ADMMB_E_BADARG;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!h->uploaded) return fail(h, ADMMB_E_STATE, "admmb_shift_resolve called before admmb_upload");
+        for (auto &s : h->shards) {
+            if (s.batch > 0 && !s.ran) return fail(h, ADMMB_E_STATE, "admmb_shift_resolve called before a solve (admmb_run)");
+            if (s.batch > 0 && s.use_dense) return fail(h, ADMMB_E_BADARG, "admmb_shift_resolve needs the Riccati path (xupdate = auto / riccati)");
+            if (s.batch > 0 && (k < 1 || k > s.N)) return fail(h, ADMMB_E_BADARG, "shift k = %d outside 1 .. N", (int)k);
+        }
+        int rc = guarded(h, [&]() {
+            for_each_shard(h, [&](int g) {
+                Shard &s = h->shards[g];
+                if (s.batch > 0 && s.uploaded) s.shift_warm_start(k, s0_new);
+            });
+            return (int)ADMMB_OK;
+        });
+        if (rc != ADMMB_OK) return rc;
+    }
+    return admmb_run(h, op, res);
 }
 
 int admmb_download(admmb_handle h, admmb_result *res)

@@ -213,6 +213,16 @@ class Solver:
         return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches),
                     kernel_ms=r.kernel_ms, kernel_launches=int(r.kernel_launches))
 
+    def shift_resolve(self, k: int, opts: dict | L.Opts, s0_new=None) -> dict:
+        """Receding-horizon step on the resident batch: warm start = the last solution shifted by k stages, initial states
+        = s0_new [batch, 6] (None: the solution's state at stage k); solves again without re-uploading the model."""
+        op = opts if isinstance(opts, L.Opts) else make_opts(opts)
+        r = L.Result()
+        s0c = None if s0_new is None else np.ascontiguousarray(s0_new, dtype=np.float64)
+        self._check(self._L.admmb_shift_resolve(self._h, int(k), _dp(s0c), C.byref(op), C.byref(r)))
+        return dict(stats=list(r.stats), device_ms=r.device_ms, launches=int(r.launches),
+                    kernel_ms=r.kernel_ms, kernel_launches=int(r.kernel_launches))
+
     def download(self, opts: dict | None = None, want=("x", "z", "u")):
         # the history buffers are sized by the UPLOADED options (the library writes max_iter_uploaded x batch values)
         max_iter, history = getattr(self, "_up", None) or (make_opts(opts).max_iter, bool(make_opts(opts).history))

@@ -156,6 +156,12 @@ int admmb_solve(admmb_handle h, const admmb_problem *prob, const admmb_opts *opt
 int admmb_upload(admmb_handle h, const admmb_problem *prob, const admmb_opts *opts);
 int admmb_run(admmb_handle h, const admmb_opts *opts, admmb_result *stats_only);
 int admmb_download(admmb_handle h, admmb_result *res);
+/* receding-horizon step on the resident batch: the (z, u) of the solve just done, shifted by k stages
+ * (stage j starts from stage j+k; the last k stages from zero; terminal blocks keep theirs), become the warm start,
+ * the initial states become s0_new [6 x batch] (NULL: the solution's own state at stage k), and the batch is solved
+ * again without any re-upload of the model.  Riccati path only.  Equivalent to admmb_solve with z0 / u0 / s0 set so. */
+int admmb_shift_resolve(admmb_handle h, int32_t k, const double *s0_new, const admmb_opts *opts,
+                        admmb_result *stats_only);
 /* launch the device work of GPU 0 on a caller-owned cudaStream_t (NULL: the library's own) */
 int admmb_set_stream(admmb_handle h, void *cuda_stream);
 

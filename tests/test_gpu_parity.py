@@ -331,3 +331,29 @@ def test_full_width_65536_to_tolerance(solver, cpu_oracle, P, kernel_variant):
     prob, opts = P.cfg2_cw_batch(batch=65536, N=50, seed=1002)
     h = _slices_vs_oracle(solver, cpu_oracle, prob, opts, "65,536 x N=50, to tolerance")
     assert (h["status"] == 0).mean() > 0.999
+
+
+# ---- receding-horizon step on the resident batch: admmb_shift_resolve against the oracle's warm-started solve
+@pytest.mark.parametrize("k,from_solution", [(1, True), (1, False), (3, False)])
+def test_shift_resolve_matches_oracle_warm_start(pkg, cpu_oracle, P, k, from_solution, kernel_variant):
+    N = 20
+    prob, opts = P.cfg2_cw_batch(batch=96, N=N, seed=5)
+    opts = dict(opts, rho=1.0, alpha=1.6, max_iter=2500)
+    with pkg.Solver() as s:
+        s.upload(prob, opts)
+        s.run(opts)
+        x, z, u, h = s.download(opts)
+        s0n = np.ascontiguousarray(x[:, 9 * k:9 * k + 6]) if from_solution else \
+            np.ascontiguousarray(x[:, 9 * k:9 * k + 6] + 1e-3)
+        s.shift_resolve(k, opts, s0_new=None if from_solution else s0n)
+        got = s.download(opts)
+
+    def shifted(a):
+        out = np.zeros_like(a)
+        out[:, :9 * (N - k)] = a[:, 9 * k:9 * N]
+        out[:, 9 * N:] = a[:, 9 * N:]
+        return out
+
+    ref = cpu_oracle.solve(dict(prob, s0=s0n, z0=shifted(z), u0=shifted(u)), opts)
+    assert (ref[3]["status"] == 0).sum() > 0
+    assert_bit_identical(got, ref, f"shift_resolve k={k}")
