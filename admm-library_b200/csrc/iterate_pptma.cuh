@@ -16,7 +16,7 @@ namespace admmb {
 // slot = [rows][32 lanes] doubles: 46 record rows + 6 (chat / c).  Always 52 rows: with the smaller 46-row slots two
 // CTAs fit an SM, the block scheduler co-locates them while other SMs idle, and the kernel gets 8 % slower (measured).
 __host__ __device__ constexpr int ppt_slot_bytes(bool) { return 52 * 256; }
-constexpr int PPT_WARPS = 4;
+constexpr int PPT_SLOTS = 8;                       // ring slots per CTA = warps x slots per warp: (4, 2) or (1, 8)
 
 struct PpTmaMaps {
     CUtensorMap m46, m10, m30, m6;                 // boxes of 46 / 10 / 30 / 6 rows x 32 columns over fac_dec [FD*N][ld]
@@ -28,52 +28,65 @@ __device__ __forceinline__ void ppt_tma(uint32_t dst, const CUtensorMap *map, in
                  ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 
-template <bool HAS_C>
+// R = slots of a warp's ring (power of two): the stage records are requested R-1 stages ahead of the math.  Two slots
+// (one stage ahead) are enough when many warps share an SM; a lone warp -- the narrow tail of a solve, where the slowest
+// problems set the time -- needs the whole DRAM latency (~800 ns) covered by requests in flight, i.e. >= 6 stages of
+// ~150 ns, so narrow working sets run one warp per CTA with an eight-slot ring (same shared memory per CTA).
+template <bool HAS_C, int R>
 struct PpStaging {
     const PpTmaMaps *maps;
-    uint32_t slot[2], bar[2];                      // this warp's ring
+    uint32_t slot0, bar0;                          // this warp's ring
     uint32_t lane8;
     int col0, N;
     unsigned *step;                                // uses of the ring so far (warp-uniform, lives in the kernel)
     bool lane0;
 
-    // step s uses slot s & 1 with mbarrier phase (s >> 1) & 1
+    // step s uses slot s % R with mbarrier phase (s / R) & 1
+    __device__ __forceinline__ uint32_t slot(unsigned s) const { return slot0 + (s & (R - 1)) * (uint32_t)ppt_slot_bytes(HAS_C); }
+    __device__ __forceinline__ uint32_t bar(unsigned s) const { return bar0 + 8u * (s & (R - 1)); }
     __device__ __forceinline__ void issue_bwd(int k, unsigned s) const
     {
-        const uint32_t d = slot[s & 1], b = bar[s & 1];
+        const uint32_t d = slot(s), b = bar(s);
         mbar_expect_tx(b, (uint32_t)((46 + (HAS_C ? 6 : 0)) * 256));
         ppt_tma(d, &maps->m46, col0, k * FD, b);
         if (HAS_C) ppt_tma(d + 46 * 256, &maps->m6, col0, k * FD + D_CHAT, b);
     }
     __device__ __forceinline__ void issue_fwd(int k, unsigned s) const
     {
-        const uint32_t d = slot[s & 1], b = bar[s & 1];
+        const uint32_t d = slot(s), b = bar(s);
         mbar_expect_tx(b, (uint32_t)((40 + (HAS_C ? 6 : 0)) * 256));
         ppt_tma(d, &maps->m10, col0, k * FD, b);
         ppt_tma(d + 10 * 256, &maps->m30, col0, k * FD + D_AIN, b);
         if (HAS_C) ppt_tma(d + 40 * 256, &maps->m6, col0, k * FD + D_C, b);
     }
+    // q-th stage of an iteration: backward stages N-1 .. 0, then forward stages 0 .. N-1
+    __device__ __forceinline__ void issue(int q, unsigned s) const
+    {
+        if (q < N) issue_bwd(N - 1 - q, s);
+        else if (q < 2 * N) issue_fwd(q - N, s);
+    }
     template <class FR>
     __device__ __forceinline__ void iter_begin(FR &)
     {
         __syncwarp();
-        if (lane0) issue_bwd(N - 1, *step);        // nothing is prefetched across iterations: the factor may have
-    }                                              // been rewritten (adaptive rho) between them
+        if (lane0)                                 // nothing is prefetched across iterations: the factor may have
+            for (int j = 0; j < R - 1; ++j) issue(j, *step + j);   // been rewritten (adaptive rho) between them
+    }
     template <class FR>
     __device__ __forceinline__ void bwd_begin(int k, FR &F)
     {
         const unsigned s = *step;
-        if (lane0) { if (k > 0) issue_bwd(k - 1, s + 1); else issue_fwd(0, s + 1); }
-        mbar_wait(bar[s & 1], (s >> 1) & 1u);
-        F.sbase = slot[s & 1] + lane8;
+        if (lane0) issue(N - 1 - k + R - 1, s + R - 1);
+        mbar_wait(bar(s), (s / R) & 1u);
+        F.sbase = slot(s) + lane8;
     }
     template <class FR>
     __device__ __forceinline__ void fwd_begin(int k, FR &F)
     {
         const unsigned s = *step;
-        if (lane0 && k + 1 < N) issue_fwd(k + 1, s + 1);
-        mbar_wait(bar[s & 1], (s >> 1) & 1u);
-        F.sbase = slot[s & 1] + lane8;
+        if (lane0) issue(N + k + R - 1, s + R - 1);
+        mbar_wait(bar(s), (s / R) & 1u);
+        F.sbase = slot(s) + lane8;
     }
     __device__ __forceinline__ void stage_end()
     {
@@ -82,10 +95,11 @@ struct PpStaging {
     }
 };
 
-// dynamic smem: [16 B mbarrier][par shared ? 8*nb doubles : 0][nb ints, padded][PPT_WARPS x 2 ring mbarriers]
-//               [pad to 128][PPT_WARPS x 2 slots of ppt_slot_bytes(HAS_C)]
-template <bool HAS_C, bool HAS_Q, bool ADAPT>
-__global__ void __launch_bounds__(PPT_WARPS * 32, 1)
+// dynamic smem: [16 B mbarrier][par shared ? 8*nb doubles : 0][nb ints, padded][PPT_SLOTS ring mbarriers]
+//               [pad to 128][PPT_SLOTS slots of ppt_slot_bytes(HAS_C)]
+// W warps per CTA, each with a ring of R = PPT_SLOTS / W slots
+template <bool HAS_C, bool HAS_Q, bool ADAPT, int W>
+__global__ void __launch_bounds__(W * 32, 1)
 k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant__ PpTmaMaps maps)
 {
     extern __shared__ __align__(128) unsigned char ppt_smem[];
@@ -97,11 +111,12 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
     const uint32_t bd_bytes = (uint32_t)(((P.nb + 3) / 4) * 16);
     const uint32_t bd_sbase = (uint32_t)__cvta_generic_to_shared(bdS);
     const uint32_t ring_bars = bd_sbase + bd_bytes;
-    const uint32_t ring = (ring_bars + PPT_WARPS * 2 * 8 + 127u) & ~127u;
+    constexpr int R = PPT_SLOTS / W;
+    const uint32_t ring = (ring_bars + PPT_SLOTS * 8 + 127u) & ~127u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
-        for (int i = 0; i < PPT_WARPS * 2; ++i)
+        for (int i = 0; i < PPT_SLOTS; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bars + 8u * i) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -130,12 +145,10 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
     F.ld = P.ld;
     F.sbase = 0;
     unsigned step = 0;
-    PpStaging<HAS_C> stg;
+    PpStaging<HAS_C, R> stg;
     stg.maps = &maps;
-    stg.slot[0] = ring + (uint32_t)(warp * 2) * ppt_slot_bytes(HAS_C);
-    stg.slot[1] = stg.slot[0] + ppt_slot_bytes(HAS_C);
-    stg.bar[0] = ring_bars + 8u * (warp * 2);
-    stg.bar[1] = stg.bar[0] + 8u;
+    stg.slot0 = ring + (uint32_t)(warp * R) * ppt_slot_bytes(HAS_C);
+    stg.bar0 = ring_bars + 8u * (warp * R);
     stg.lane8 = 8u * lane;
     stg.col0 = col0;
     stg.N = P.N;
@@ -166,7 +179,7 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
         const bool run = st == ST_RUNNING;
         if (!__any_sync(0xffffffffu, run)) break;
         double nr[5];
-        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
+        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C, R>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
         if (!run) continue;
         ++it;
         sigma = 1.0;

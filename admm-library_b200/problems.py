@@ -271,7 +271,7 @@ def cfg4_elliptic(batch: int = 16384, N: int = 50, seed: int = 4,
                   a_max: float = 10.0, e_max: float = 0.5) -> tuple[dict, dict]:
     """configs[3]: elliptic-orbit rendezvous with per-problem time-varying STMs (Riccati path).
     e ~ U(0.05, 0.5), a_max = 10: with round 1's e up to 0.7 and a_max = 3 a quarter of the problems were infeasible
-    (thrust saturated on every stage).  rho, alpha tuned once with the oracle: all converge, median 1,700 iterations."""
+    (thrust saturated on every stage).  rho, alpha tuned once with the oracle: all of 256 converge (median 1,700 iterations, 99 % below 6,500); of 16,384, 99.6 % by 15,000 and all but 2 by 40,000."""
     rng = np.random.Generator(np.random.PCG64(seed))
     e = rng.uniform(0.05, e_max, batch)
     th0 = rng.uniform(0.0, 2.0 * np.pi, batch)
@@ -281,7 +281,7 @@ def cfg4_elliptic(batch: int = 16384, N: int = 50, seed: int = 4,
     s0 = S0_NOMINAL[None, :] + S0_SIGMA[None, :] * rng.standard_normal((batch, 6))
     prob = dict(N=N, A=A, B=B, c=None, Q=None, R=None, q=None,
                 s0=s0, block_type=bt, block_par=bp, meta=dict(e=e, theta0=th0))
-    opts = dict(DEFAULT_OPTS, rho=0.05, alpha=1.6, max_iter=15000)
+    opts = dict(DEFAULT_OPTS, rho=0.05, alpha=1.6, max_iter=30000)
     return prob, opts
 
 

@@ -16,7 +16,7 @@ pkg = graft.load_pkg()
 if os.environ.get("ADMMB_LIB"):          # developer build of the library (e.g. -DWG_TIMING in lib_timing/)
     pkg._lib.LIB_PATH = os.path.abspath(os.environ["ADMMB_LIB"])
 P = pkg.problems
-gen = {"cfg2": P.cfg2_cw_batch, "cfg3": P.cfg3_lowthrust_soc, "cfg5": P.cfg5_montecarlo}[name]
+gen = {"cfg2": P.cfg2_cw_batch, "cfg3": P.cfg3_lowthrust_soc, "cfg4": P.cfg4_elliptic, "cfg5": P.cfg5_montecarlo}[name]
 for w in widths:
     prob, opts = gen(w)
     for v in variants:
