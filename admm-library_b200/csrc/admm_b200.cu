@@ -317,14 +317,18 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     uploaded = true;
 }
 
-// Widest working set the warp-group kernel takes when the choice is the library's.  Measured on B200 (cfg2, N = 50,
-// scripts/variant_rates.py): the warp-group kernel runs 4.1e8 problem-iterations/s at any width >= 4,096 and 10 us per
-// iteration below; one problem per thread needs 32 us per iteration up to 16,384 problems (2.6e8 at 8,192, 4.8e8 at
-// 16,384), so the two cross between 12 k and 14 k problems.  (Tuning knob; it has no effect on results.)
-static int64_t wg_max_width()
+// Widest working set the warp-group kernel takes when the choice is the library's, in PASSES (tiles per CTA).  Measured on
+// B200 (scripts/variant_rates.py): a warp-group iteration costs ~0.2 us per stage and pass (9.9 us at N = 50), one problem
+// per thread ~0.64 us per stage at any width up to ~16 k problems (32 us at N = 50), so the warp-group kernel wins up to
+// three passes: 13,320 problems at N = 50 (30 problems per tile), 5,328 at N = 100 (12 per tile).  ADMMB_WG_WIDTH caps the
+// width in problems instead (tuning knob; neither has any effect on results).
+static bool wg_takes(int64_t n_active, int tile, int num_sms)
 {
-    static const int64_t w = getenv("ADMMB_WG_WIDTH") ? atoll(getenv("ADMMB_WG_WIDTH")) : 12288;
-    return w;
+    static const int64_t w = getenv("ADMMB_WG_WIDTH") ? atoll(getenv("ADMMB_WG_WIDTH")) : -1;
+    if (tile <= 0) return false;
+    if (w >= 0) return n_active <= w;
+    const int64_t tiles = (n_active + tile - 1) / tile;
+    return (tiles + num_sms - 1) / num_sms <= 3;
 }
 
 template <bool FSH, bool FSMEM>
@@ -335,7 +339,7 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
                     rows_zu, device, time_invariant};
     last_kernel = KV_THREAD;
     if (FSH && FSMEM) {
-        const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && P.n_active <= wg_max_width());
+        const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && wg_takes(P.n_active, iterate_wg_tile_width(c), num_sms));
         const bool tile = kernel_variant == KV_TILE;
         if (wg && launch_iterate_wg(c, P, adapt)) last_kernel = KV_WG;
         else if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
