@@ -473,3 +473,41 @@ def test_tf32_condensed_variants(solver, cpu_oracle, P, variant):
     if prob.get("c") is not None:
         res = res - np.asarray(prob["c"])[0][None]
     assert np.abs(res).max() <= 1e-12 * sx
+
+
+@pytest.mark.gpu
+def test_run_rejects_options_that_contradict_the_upload(pkg, P):
+    """admmb_run must not accept options that change what admmb_upload built on the device (a shared factor
+    computed for one rho with per-problem adaptive rho, history buffers of another size, another x-update)."""
+    prob, opts = P.lqr_tracking(batch=16, N=8, seed=3)            # Q, R present: the factor depends on rho
+    with pkg.Solver() as s:
+        s.upload(prob, dict(opts, adapt_rho=0, history=0))
+        s.run(dict(opts, adapt_rho=0, history=0, rho=2.0, alpha=1.2, max_iter=77))      # free to vary
+        for bad in (dict(adapt_rho=1), dict(history=1), dict(xupdate="dense"), dict(rho=-1.0), dict(alpha=2.5)):
+            with pytest.raises(pkg._lib.AdmmError) as e:
+                s.run({**opts, "adapt_rho": 0, "history": 0, **bad})
+            assert e.value.code == pkg._lib.E_BADARG, bad
+        s.upload(prob, dict(opts, history=1, max_iter=50))
+        with pytest.raises(pkg._lib.AdmmError):
+            s.run(dict(opts, history=1, max_iter=60))
+
+
+@pytest.mark.gpu
+def test_history_of_iterations_never_run_is_nan_on_the_c_abi(pkg, P):
+    """callers of the C ABI / MEX gateway get the history as the device wrote it; entries of iterations a
+    problem never ran must be NaN (as in the oracle), not stale device memory."""
+    prob, opts = P.cfg2_cw_batch(batch=40, N=10, seed=9)
+    o = dict(opts, rho=1.0, alpha=1.6, max_iter=300, history=1)
+    with pkg.Solver() as s:
+        for _ in range(2):                                         # second run: the buffer holds an older history
+            s.upload(prob, o)
+            s.run(o)
+            res = pkg.solver.ResultBuffers(40, 96, 300, True)
+            for v in res.hist.values():
+                v[:] = 0.0                                         # not NaN: whatever is NaN afterwards came from the device
+            s.download_c(res.c)
+            it = res.iters
+            k = np.arange(300)[None, :]
+            for name, v in res.hist.items():
+                assert np.isnan(v[k >= it[:, None]]).all(), name
+                assert np.isfinite(v[k < it[:, None]]).all(), name
