@@ -18,7 +18,8 @@ ERROR_NAMES = {E_BADARG: "ADMMB_E_BADARG", E_CUDA: "ADMMB_E_CUDA", E_NCCL: "ADMM
 EXPORTS = ["admmb_version", "admmb_create", "admmb_destroy", "admmb_last_error", "admmb_device_count",
            "admmb_solve", "admmb_upload", "admmb_run", "admmb_download", "admmb_set_stream", "admmb_shift_resolve",
            "admmb_k_riccati_factor", "admmb_k_xupdate_riccati", "admmb_k_prox_dual_residuals",
-           "admmb_k_dense_factor", "admmb_k_xupdate_dense"]
+           "admmb_k_dense_factor", "admmb_k_xupdate_dense",
+           "admmb_upload_generated", "admmb_solve_generated", "admmb_k_generate"]
 
 
 class Problem(C.Structure):
@@ -26,6 +27,11 @@ class Problem(C.Structure):
                 ("B", c_dp), ("c", c_dp), ("Q", c_dp), ("R", c_dp), ("q", c_dp), ("q_batched", C.c_int32),
                 ("s0", c_dp), ("block_type", c_ip), ("block_par", c_dp), ("par_batched", C.c_int32),
                 ("z0", c_dp), ("u0", c_dp), ("rho0", c_dp)]
+
+
+class Generator(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("substeps", C.c_int32), ("T", C.c_double), ("nmm", C.c_double),
+                ("e", c_dp), ("theta0", c_dp)]
 
 
 class Opts(C.Structure):
@@ -82,6 +88,9 @@ def load() -> C.CDLL:
                                               C.c_double, c_dp, c_dp, c_dp, c_dp]
     L.admmb_k_dense_factor.argtypes = [H, C.c_int32, c_dp, C.c_int32, c_dp, c_dp, c_dp]
     L.admmb_k_xupdate_dense.argtypes = [H, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp]
+    L.admmb_upload_generated.argtypes = [H, C.POINTER(Problem), C.POINTER(Generator), C.POINTER(Opts)]
+    L.admmb_solve_generated.argtypes = [H, C.POINTER(Problem), C.POINTER(Generator), C.POINTER(Opts), C.POINTER(Result)]
+    L.admmb_k_generate.argtypes = [H, C.c_int32, C.c_int64, C.POINTER(Generator), c_dp, c_dp]
     for name in EXPORTS:
         if name not in ("admmb_last_error",):
             getattr(L, name).restype = C.c_int

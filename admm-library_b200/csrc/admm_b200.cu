@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "iterate_launch_decl.cuh"
 #include "dense.cuh"
+#include "generators.cuh"
 
 using namespace admmb;
 
@@ -178,7 +179,10 @@ struct Shard {
         CK(cudaMemcpyAsync(host, stg.p, sizeof(T) * (size_t)batch * R, cudaMemcpyDeviceToHost, stream));
     }
 
-    void upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt);
+    void upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt, const admmb_generator *gen);
+    void generate_model(const admmb_generator *gen, int64_t begin, int64_t cnt, int N_, size_t ld_, double *A, double *B,
+                        DevBuf<double> &par_e, DevBuf<double> &par_th);
+    DevBuf<double> gen_e, gen_th;
     void run(const admmb_opts *op, admmb_result *res);
     void download(admmb_result *res);
     void shift_warm_start(int k, const double *s0_new_host);
@@ -186,7 +190,26 @@ struct Shard {
     void launch_iterate(const IterParams &P, bool adapt);
 };
 
-void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt)
+// the stage matrices computed on the device (csrc/generators.cuh) into the raw-model arrays
+void Shard::generate_model(const admmb_generator *gen, int64_t begin, int64_t cnt, int N_, size_t ld_, double *A, double *B,
+                           DevBuf<double> &par_e, DevBuf<double> &par_th)
+{
+    if (gen->kind == GEN_ELLIPTIC_ZOH) {
+        par_e.alloc((size_t)cnt);
+        par_th.alloc((size_t)cnt);
+        CK(cudaMemcpyAsync(par_e.p, gen->e + begin, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(par_th.p, gen->theta0 + begin, sizeof(double) * cnt, cudaMemcpyHostToDevice, stream));
+        dim3 grid((unsigned)((cnt + 127) / 128), 9);
+        k_gen_elliptic<<<grid, 128, 0, stream>>>(par_e.p, par_th.p, cnt, N_, gen->T, gen->substeps > 0 ? gen->substeps : 8,
+                                                 A, B, ld_);
+    } else {
+        k_gen_cw<<<1, 64, 0, stream>>>(gen->kind, N_, gen->T, gen->nmm != 0.0 ? gen->nmm : 1.0, A, B);
+    }
+    ++launches;
+    CK(cudaGetLastError());
+}
+
+void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin, int64_t cnt, const admmb_generator *gen)
 {
     CK(cudaSetDevice(device));
     uploaded = false;
@@ -197,7 +220,7 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     batch = cnt;
     p_begin = begin;
     ld = round_up((size_t)cnt, 32);
-    dyn_batched = pb->dyn_batched != 0;
+    dyn_batched = gen ? gen->kind == GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0;
     has_c = pb->c != nullptr;
     has_Q = pb->Q != nullptr;
     has_R = pb->R != nullptr;
@@ -250,7 +273,7 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     }
 
     time_invariant = !dyn_batched;
-    for (int k = 1; k < N && time_invariant; ++k)
+    for (int k = 1; k < N && time_invariant && !gen; ++k)
         time_invariant = memcmp(pb->A, pb->A + (size_t)36 * k, 36 * sizeof(double)) == 0 &&
                          memcmp(pb->B, pb->B + (size_t)18 * k, 18 * sizeof(double)) == 0;
 
@@ -262,8 +285,18 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
         if (dyn_batched) upload_rows(host + (size_t)begin * R, cnt, R, buf.p, nullptr);
         else CK(cudaMemcpyAsync(buf.p, host, sizeof(double) * R, cudaMemcpyHostToDevice, stream));
     };
-    up_model(rawA, pb->A, 36 * N);
-    up_model(rawB, pb->B, 18 * N);
+    if (gen) {
+        rawA.alloc((size_t)36 * N * md);
+        rawB.alloc((size_t)18 * N * md);
+        if (dyn_batched) {   // columns beyond the batch stay finite
+            CK(cudaMemsetAsync(rawA.p, 0, sizeof(double) * 36 * N * md, stream));
+            CK(cudaMemsetAsync(rawB.p, 0, sizeof(double) * 18 * N * md, stream));
+        }
+        generate_model(gen, begin, cnt, N, ld, rawA.p, rawB.p, gen_e, gen_th);
+    } else {
+        up_model(rawA, pb->A, 36 * N);
+        up_model(rawB, pb->B, 18 * N);
+    }
     up_model(rawc, pb->c, 6 * N);
     up_model(rawQ, pb->Q, 36 * (N + 1));
     up_model(rawR, pb->R, 9 * N);
@@ -791,13 +824,28 @@ int cuda_code(cudaError_t e)
 
 int validate_opts(admmb_ctx *h, const admmb_opts *op);
 
-int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
+int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op, const admmb_generator *gen = nullptr)
 {
     if (!pb || !op) return fail(h, ADMMB_E_BADARG, "null problem/opts");
+    if (gen) {
+        if (gen->kind < ADMMB_GEN_CW_IMPULSIVE || gen->kind > ADMMB_GEN_ELLIPTIC_ZOH)
+            return fail(h, ADMMB_E_BADARG, "generator kind must be an ADMMB_GEN_* code");
+        if (!(gen->T > 0.0) || !std::isfinite(gen->T)) return fail(h, ADMMB_E_BADARG, "generator: stage length T must be > 0");
+        if (gen->substeps < 0 || gen->substeps > 4096) return fail(h, ADMMB_E_BADARG, "generator: substeps out of range");
+        if (gen->kind == ADMMB_GEN_ELLIPTIC_ZOH) {
+            if (!gen->e || !gen->theta0) return fail(h, ADMMB_E_BADARG, "generator: e and theta0 are required for ADMMB_GEN_ELLIPTIC_ZOH");
+            for (int64_t i = 0; i < pb->batch; ++i)
+                if (!(gen->e[i] >= 0.0 && gen->e[i] < 1.0) || !std::isfinite(gen->theta0[i]) || std::fabs(gen->theta0[i]) > 1.0e3)
+                    return fail(h, ADMMB_E_BADARG, "generator: problem %lld needs 0 <= e < 1 and |theta0| <= 1000", (long long)i);
+        } else if (!(gen->nmm >= 0.0) || !std::isfinite(gen->nmm)) {
+            return fail(h, ADMMB_E_BADARG, "generator: mean motion must be > 0 (0 = 1)");
+        }
+    }
     if (pb->N < 1 || pb->N > 4096) return fail(h, ADMMB_E_BADARG, "N out of range");
     if (pb->batch < 1 || pb->batch > (int64_t)1 << 30) return fail(h, ADMMB_E_BADARG, "batch out of range");
-    if (!pb->A || !pb->B || !pb->s0 || !pb->block_type || !pb->block_par)
+    if ((!gen && (!pb->A || !pb->B)) || !pb->s0 || !pb->block_type || !pb->block_par)
         return fail(h, ADMMB_E_BADARG, "A, B, s0, block_type and block_par are required");
+    const bool model_batched = gen ? gen->kind == ADMMB_GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0;
     const int nb = 3 * pb->N + 2;
     int nsplit = 0;
     for (int b = 0; b < nb; ++b) {
@@ -811,7 +859,7 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op)
             return fail(h, ADMMB_E_BADARG, "control block %d is unsplit and R is absent: x-update is singular", k);
     if (op->xupdate == ADMMB_XUPDATE_DENSE) {
         const bool has_P = pb->Q || pb->R;
-        if (pb->dyn_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
+        if (model_batched) return fail(h, ADMMB_E_BADARG, "dense x-update needs a shared model (dyn_batched = 0)");
         if (has_P && (op->adapt_rho || pb->rho0)) return fail(h, ADMMB_E_BADARG, "dense x-update with P != 0 needs one shared rho");
         if (op->history) return fail(h, ADMMB_E_BADARG, "history is not recorded on the dense path");
         if (op->adapt_rho) return fail(h, ADMMB_E_BADARG, "adaptive rho is not implemented on the dense path (use xupdate = auto / riccati)");
@@ -941,10 +989,15 @@ int admmb_set_stream(admmb_handle h, void *cuda_stream)
 
 int admmb_upload(admmb_handle h, const admmb_problem *pb, const admmb_opts *op)
 {
+    return admmb_upload_generated(h, pb, nullptr, op);
+}
+
+int admmb_upload_generated(admmb_handle h, const admmb_problem *pb, const admmb_generator *gen, const admmb_opts *op)
+{
     if (!h) return ADMMB_E_BADARG;
     std::lock_guard<std::mutex> lk(h->mu);
     h->uploaded = false;
-    int rc = validate(h, pb, op);
+    int rc = validate(h, pb, op, gen);
     if (rc != ADMMB_OK) return rc;
     const int G = (int)std::min<int64_t>((int64_t)h->shards.size(), pb->batch);
     rc = guarded(h, [&]() {
@@ -953,7 +1006,7 @@ int admmb_upload(admmb_handle h, const admmb_problem *pb, const admmb_opts *op)
             shard_range(pb->batch, G, g, b, c);
             Shard &s = h->shards[g];
             if (g >= G || c <= 0) { s.uploaded = false; s.batch = 0; return; }
-            s.upload(pb, op, b, c);
+            s.upload(pb, op, b, c, gen);
             if (s.use_dense || s.tf32_tail) dense_prepare(s, op);
         });
         return (int)ADMMB_OK;
@@ -1059,10 +1112,16 @@ int admmb_download(admmb_handle h, admmb_result *res)
 
 int admmb_solve(admmb_handle h, const admmb_problem *pb, const admmb_opts *op, admmb_result *res)
 {
+    return admmb_solve_generated(h, pb, nullptr, op, res);
+}
+
+int admmb_solve_generated(admmb_handle h, const admmb_problem *pb, const admmb_generator *gen, const admmb_opts *op,
+                          admmb_result *res)
+{
     if (!h || !res) return ADMMB_E_BADARG;
     for (auto &s : h->shards) s.launches = 0;
     auto t0 = std::chrono::steady_clock::now();
-    int rc = admmb_upload(h, pb, op);
+    int rc = admmb_upload_generated(h, pb, gen, op);
     if (rc != ADMMB_OK) return rc;
     auto t1 = std::chrono::steady_clock::now();
     rc = admmb_run(h, op, res);

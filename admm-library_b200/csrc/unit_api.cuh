@@ -184,4 +184,33 @@ int admmb_k_xupdate_dense(admmb_handle h, int32_t N, int64_t batch, const double
     });
 }
 
+int admmb_k_generate(admmb_handle h, int32_t N, int64_t batch, const admmb_generator *gen, double *A, double *B)
+{
+    if (!h || N < 1 || batch < 1 || !gen || !A || !B) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    {
+        if (gen->kind < ADMMB_GEN_CW_IMPULSIVE || gen->kind > ADMMB_GEN_ELLIPTIC_ZOH || !(gen->T > 0.0) || gen->substeps < 0 ||
+            (gen->kind == ADMMB_GEN_ELLIPTIC_ZOH && (!gen->e || !gen->theta0)))
+            return fail(h, ADMMB_E_BADARG, "admmb_k_generate: bad generator");
+    }
+    return guarded(h, [&]() {
+        UnitCtx U(h);
+        const bool pp = gen->kind == ADMMB_GEN_ELLIPTIC_ZOH;
+        const size_t ld = pp ? round_up((size_t)batch, 32) : 1;
+        DevBuf<double> dA, dB, de, dth, stg;
+        dA.alloc((size_t)36 * N * ld);
+        dB.alloc((size_t)18 * N * ld);
+        U.s.generate_model(gen, 0, batch, N, ld, dA.p, dB.p, de, dth);
+        if (pp) {
+            U.down_rows(dA.p, stg, A, batch, 36 * N, ld);
+            U.down_rows(dB.p, stg, B, batch, 18 * N, ld);
+        } else {
+            CK(cudaMemcpyAsync(A, dA.p, sizeof(double) * 36 * N, cudaMemcpyDeviceToHost, U.s.stream));
+            CK(cudaMemcpyAsync(B, dB.p, sizeof(double) * 18 * N, cudaMemcpyDeviceToHost, U.s.stream));
+            CK(cudaStreamSynchronize(U.s.stream));
+        }
+        return (int)ADMMB_OK;
+    });
+}
+
 }  // extern "C"

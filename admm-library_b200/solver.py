@@ -41,6 +41,18 @@ def pack_factor(parts, N, layout=FAC_LAYOUT, fs=FS):
     return fac
 
 
+GENERATOR = {"cw_impulsive": 1, "cw_zoh": 2, "elliptic_zoh": 3}   # include/admm_b200.h ADMMB_GEN_*
+
+
+def make_generator(gen: dict):
+    """gen = dict(kind=..., T=..., nmm=1.0, substeps=8, e=[batch], theta0=[batch]) -> (ctypes struct, buffers to keep alive)."""
+    e = None if gen.get("e") is None else np.ascontiguousarray(gen["e"], dtype=np.float64)
+    th = None if gen.get("theta0") is None else np.ascontiguousarray(gen["theta0"], dtype=np.float64)
+    g = L.Generator(kind=GENERATOR[gen["kind"]], substeps=int(gen.get("substeps", 0)), T=float(gen["T"]),
+                    nmm=float(gen.get("nmm", 0.0)), e=_dp(e), theta0=_dp(th))
+    return g, (e, th)
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(L.c_dp)
 
@@ -55,15 +67,18 @@ def to_c_layout(prob: dict) -> dict:
     t = lambda a: None if a is None else np.ascontiguousarray(  # noqa: E731
         np.swapaxes(np.asarray(a, dtype=np.float64), -1, -2))
     Bsz = int(prob["s0"].shape[0])
-    Bd = int(prob["A"].shape[0])
+    if prob.get("A") is None:     # generated model (Solver.solve_generated): A, B are computed on the device
+        Bd, N = 1, int(prob["N"])
+    else:
+        Bd, N = int(prob["A"].shape[0]), int(prob["A"].shape[1])
     if Bd not in (1, Bsz):
         raise ValueError("A leading dimension must be 1 (shared) or batch")
     for k in ("B", "c", "Q", "R"):
         a = prob.get(k)
-        if a is not None and a.shape[0] != Bd:
+        if a is not None and prob.get("A") is not None and a.shape[0] != Bd:
             raise ValueError(f"{k} must be batched like A")
-    m = dict(N=int(prob["A"].shape[1]), batch=Bsz, dyn_batched=int(Bd > 1),
-             A=t(prob["A"]), B=t(prob["B"]), c=f(prob.get("c")), Q=t(prob.get("Q")), R=t(prob.get("R")),
+    m = dict(N=N, batch=Bsz, dyn_batched=int(Bd > 1),
+             A=t(prob.get("A")), B=t(prob.get("B")), c=f(prob.get("c")), Q=t(prob.get("Q")), R=t(prob.get("R")),
              q=f(prob.get("q")), s0=f(prob["s0"]),
              block_type=np.ascontiguousarray(prob["block_type"], dtype=np.int32),
              block_par=f(prob["block_par"]), z0=f(prob.get("z0")), u0=f(prob.get("u0")),
@@ -188,6 +203,37 @@ class Solver:
         pb = make_problem(m)
         self._check(self._L.admmb_solve(self._h, C.byref(pb), C.byref(op), C.byref(res.c)))
         return res.x, res.z, res.u, res.hist_dict()
+
+    def solve_generated(self, prob: dict, gen: dict, opts: dict, want=("x", "z", "u")):
+        """solve() with the stage matrices generated on the device: prob carries N instead of A, B."""
+        m = to_c_layout(prob)
+        n = 9 * m["N"] + 6
+        op = make_opts(opts)
+        res = ResultBuffers(m["batch"], n, op.max_iter, bool(op.history), want)
+        pb = make_problem(m)
+        g, keep = make_generator(gen)
+        self._check(self._L.admmb_solve_generated(self._h, C.byref(pb), C.byref(g), C.byref(op), C.byref(res.c)))
+        return res.x, res.z, res.u, res.hist_dict()
+
+    def upload_generated(self, prob: dict, gen: dict, opts: dict):
+        m = to_c_layout(prob)
+        self._keep = m
+        self._n = 9 * m["N"] + 6
+        self._batch = m["batch"]
+        pb = make_problem(m)
+        op = make_opts(opts)
+        g, keep = make_generator(gen)
+        self._check(self._L.admmb_upload_generated(self._h, C.byref(pb), C.byref(g), C.byref(op)))
+        self._up = (int(op.max_iter), bool(op.history))
+
+    def k_generate(self, N: int, batch: int, gen: dict):
+        """The generated stage matrices in math layout: A (Bd,N,6,6), B (Bd,N,6,3)."""
+        g, keep = make_generator(gen)
+        Bd = batch if gen["kind"] == "elliptic_zoh" else 1
+        A = np.zeros((Bd, N, 6, 6))     # column-major 6x6 per stage on the C side: transposed below
+        B = np.zeros((Bd, N, 3, 6))
+        self._check(self._L.admmb_k_generate(self._h, int(N), int(batch), C.byref(g), _dp(A), _dp(B)))
+        return np.ascontiguousarray(np.swapaxes(A, -1, -2)), np.ascontiguousarray(np.swapaxes(B, -1, -2))
 
     # ---- staged ----------------------------------------------------------------------------
     def upload(self, prob: dict, opts: dict):

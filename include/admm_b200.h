@@ -162,6 +162,30 @@ int admmb_download(admmb_handle h, admmb_result *res);
  * again without any re-upload of the model.  Riccati path only.  Equivalent to admmb_solve with z0 / u0 / s0 set so. */
 int admmb_shift_resolve(admmb_handle h, int32_t k, const double *s0_new, const admmb_opts *opts,
                         admmb_result *stats_only);
+/* ---- on-device problem generators ----------------------------------------------------------------
+ * The stage matrices A_k, B_k are computed on the GPU from a few parameters instead of being uploaded: a per-problem
+ * model is 54 N doubles per problem over PCIe (354 MB for 16,384 problems at N = 50), its parameters are 16 B.
+ * Oracle: oracle/gen_ocp.py (same IEEE operations in the same order; outputs are bit-identical). */
+enum {
+    ADMMB_GEN_CW_IMPULSIVE = 1,  /* shared model: A = Phi_CW(T), B = Phi_CW(T)[:, 3:6]            (closed form)     */
+    ADMMB_GEN_CW_ZOH = 2,        /* shared model: A = Phi_CW(T), B = int_0^T Phi_CW [0; I]        (closed form)     */
+    ADMMB_GEN_ELLIPTIC_ZOH = 3   /* per-problem, time-varying: RK4 of the LVLH dynamics linearised about a Kepler
+                                    orbit of eccentricity e[p] from true anomaly theta0[p], zero-order-hold input    */
+};
+typedef struct admmb_generator {
+    int32_t kind;                /* ADMMB_GEN_*                                                  */
+    int32_t substeps;            /* ELLIPTIC: RK4 steps per stage (0 = 8)                       */
+    double T;                    /* stage length (time unit 1 / mean motion)                    */
+    double nmm;                  /* CW kinds: mean motion (0 = 1)                               */
+    const double *e;             /* ELLIPTIC: [batch] eccentricities, 0 <= e < 1                */
+    const double *theta0;        /* ELLIPTIC: [batch] true anomaly at the start of stage 0      */
+} admmb_generator;
+/* admmb_upload / admmb_solve with prob->A, prob->B and prob->dyn_batched ignored (A, B may be NULL): the model comes
+ * from `gen`; c, Q, R must then be shared (or NULL) for the CW kinds and per-problem (or NULL) for ELLIPTIC. */
+int admmb_upload_generated(admmb_handle h, const admmb_problem *prob, const admmb_generator *gen,
+                           const admmb_opts *opts);
+int admmb_solve_generated(admmb_handle h, const admmb_problem *prob, const admmb_generator *gen,
+                          const admmb_opts *opts, admmb_result *res);
 /* launch the device work of GPU 0 on a caller-owned cudaStream_t (NULL: the library's own) */
 int admmb_set_stream(admmb_handle h, void *cuda_stream);
 
@@ -184,6 +208,10 @@ int admmb_k_dense_factor(admmb_handle h, int32_t N, const double *fac, int32_t h
 int admmb_k_xupdate_dense(admmb_handle h, int32_t N, int64_t batch, const double *M, const double *S,
                           const double *mc, const double *s0, const double *rt, int32_t precision,
                           double *x);
+
+/* the generated stage matrices themselves, A [6x6xNxBd], B [6x3xNxBd] (Bd = 1 for the CW kinds, batch
+ * for ELLIPTIC), for comparison with oracle/gen_ocp.py                                              */
+int admmb_k_generate(admmb_handle h, int32_t N, int64_t batch, const admmb_generator *gen, double *A, double *B);
 
 #ifdef __cplusplus
 }

@@ -511,3 +511,75 @@ def test_history_of_iterations_never_run_is_nan_on_the_c_abi(pkg, P):
             for name, v in res.hist.items():
                 assert np.isnan(v[k >= it[:, None]]).all(), name
                 assert np.isfinite(v[k < it[:, None]]).all(), name
+
+
+# ---- on-device generators ---------------------------------------------------------------------------
+GEN_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "generators", "*_*.npz")))
+
+
+@pytest.mark.parametrize("path", [g for g in GEN_GOLDEN if "sincos" not in g],
+                         ids=[os.path.basename(g)[:-4] for g in GEN_GOLDEN if "sincos" not in g])
+def test_generator_kernels_reproduce_golden_fixtures_bit_for_bit(solver, path):
+    g = np.load(path)
+    kind = str(g["kind"])
+    gen = dict(kind=kind, T=float(g["T"]))
+    if kind == "elliptic_zoh":
+        gen.update(e=g["e"], theta0=g["theta0"], substeps=int(g["substeps"]))
+        batch = len(g["e"])
+    else:
+        gen.update(nmm=float(g["nmm"]))
+        batch = 1
+    A, B = solver.k_generate(int(g["N"]), batch, gen)
+    assert np.array_equal(A, g["A"]), f"A differs: {np.abs(A - g['A']).max():.3e}"
+    assert np.array_equal(B, g["B"]), f"B differs: {np.abs(B - g['B']).max():.3e}"
+
+
+@pytest.mark.parametrize("batch,N,sub", [(1, 1, 1), (33, 3, 8), (257, 50, 8), (4096, 20, 4)])
+def test_generator_elliptic_matches_oracle_generator(solver, batch, N, sub):
+    from oracle import gen_ocp as G
+    rng = np.random.Generator(np.random.PCG64(100 + batch))
+    e, th = rng.uniform(0.0, 0.75, batch), rng.uniform(-7.0, 7.0, batch)
+    T = 2 * np.pi / N
+    A, B = solver.k_generate(N, batch, dict(kind="elliptic_zoh", T=T, e=e, theta0=th, substeps=sub))
+    Ar, Br = G.elliptic_stage_matrices(e, th, N, T, sub)
+    assert np.array_equal(A, Ar) and np.array_equal(B, Br)
+
+
+@pytest.mark.parametrize("kind", ["elliptic_zoh", "cw_impulsive", "cw_zoh"])
+def test_solve_generated_equals_solve_with_uploaded_oracle_matrices(solver, cpu_oracle, P, kind):
+    """The generated model feeds the same factor / iteration kernels: the solve is bit-identical to the oracle's solve
+    of the problem whose (A, B) come from the oracle generator."""
+    from oracle import gen_ocp as G
+    if kind == "elliptic_zoh":
+        prob, opts = P.cfg4_elliptic(batch=97, N=14, seed=41)
+        gen = dict(kind=kind, T=2 * np.pi / 14, e=prob["meta"]["e"], theta0=prob["meta"]["theta0"])
+        A, B = G.elliptic_stage_matrices(gen["e"], gen["theta0"], 14, gen["T"], 8)
+        opts = dict(opts, max_iter=400)
+    elif kind == "cw_zoh":
+        prob, opts = P.cfg3_lowthrust_soc(batch=130, N=16, seed=42)
+        gen = dict(kind=kind, T=2 * np.pi / 16)
+        A, B = G.cw_stage_matrices(kind, 16, gen["T"])
+        opts = dict(opts, max_iter=500)
+    else:
+        prob, opts = P.cfg2_cw_batch(batch=130, N=16, seed=43)
+        gen = dict(kind=kind, T=2 * np.pi / 16)
+        A, B = G.cw_stage_matrices(kind, 16, gen["T"])
+        opts = dict(opts, max_iter=500)
+    ref_prob = dict(prob, A=A, B=B)
+    ref = cpu_oracle.solve(ref_prob, opts)
+    gen_prob = {k: v for k, v in prob.items() if k not in ("A", "B", "meta")}
+    gen_prob["N"] = ref_prob["A"].shape[1]
+    got = solver.solve_generated(gen_prob, gen, opts)
+    assert_bit_identical(got, ref, f"generated {kind}")
+    assert_bit_identical(solver.solve(ref_prob, opts), ref, f"uploaded {kind}")
+
+
+def test_generator_bad_arguments(solver, pkg, P):
+    prob, opts = P.cfg2_cw_batch(batch=8, N=5, seed=1)
+    gp = {k: v for k, v in prob.items() if k not in ("A", "B")}
+    gp["N"] = 5
+    for gen in (dict(kind="elliptic_zoh", T=0.1), dict(kind="cw_zoh", T=-1.0),
+                dict(kind="elliptic_zoh", T=0.1, e=np.full(8, 1.5), theta0=np.zeros(8))):
+        with pytest.raises(pkg._lib.AdmmError) as ei:
+            solver.solve_generated(gp, gen, opts)
+        assert ei.value.code == pkg._lib.E_BADARG

@@ -262,3 +262,44 @@ def test_split_free_formulation_converges_to_same_solution_slower(P, cpu_oracle)
     assert h1["status"][0] == 0 and h2["status"][0] == 0
     assert h2["iters"][0] > 2 * h1["iters"][0]
     assert abs(O.objective(prob, z1)[0] - O.objective(prob, z2)[0]) < 1e-4
+
+
+# ---- generator oracle: oracle/gen_ocp.py is the spelled-out-order statement the device generators follow ----
+GEN_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "generators", "*.npz")))
+
+
+def test_det_sincos_is_accurate_and_reproduces_its_fixture():
+    from oracle import gen_ocp as G
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "generators", "det_sincos.npz"))
+    s, c = G.det_sincos(g["x"])
+    assert np.array_equal(s, g["s"]) and np.array_equal(c, g["c"])           # same bits on every machine
+    assert np.abs(s - np.sin(g["x"])).max() <= 4e-16 and np.abs(c - np.cos(g["x"])).max() <= 4e-16
+
+
+def test_generator_oracle_matches_problem_generators(P):
+    """gen_ocp (fixed operation order, polynomial trig) against problems.py (NumPy matmul, libm trig)."""
+    from oracle import gen_ocp as G
+    for T, nmm in ((2 * np.pi / 50, 1.0), (0.37, 1.3), (2 * np.pi / 20, 0.8)):
+        assert np.abs(G.cw_stm(T, nmm) - P.cw_stm(T, nmm)).max() <= 1e-14
+        Pg, Gg = G.cw_zoh(T, nmm)
+        Pp, Gp = P.cw_zoh(T, nmm)
+        assert np.abs(Pg - Pp).max() <= 1e-14 and np.abs(Gg - Gp).max() <= 1e-14
+    rng = np.random.default_rng(5)
+    e, th = rng.uniform(0.0, 0.7, 40), rng.uniform(0, 2 * np.pi, 40)
+    A, B = G.elliptic_stage_matrices(e, th, 12, 2 * np.pi / 12, 8)
+    A2, B2 = P.elliptic_stage_matrices(e, th, 12, 2 * np.pi / 12, 8)
+    assert np.abs(A - A2).max() <= 1e-13 * np.abs(A2).max() and np.abs(B - B2).max() <= 1e-13 * np.abs(B2).max()
+
+
+@pytest.mark.parametrize("path", GEN_GOLDEN, ids=[os.path.basename(g)[:-4] for g in GEN_GOLDEN])
+def test_generator_oracle_reproduces_golden_fixtures(path):
+    from oracle import gen_ocp as G
+    g = np.load(path)
+    if "kind" not in g.files:
+        return
+    kind = str(g["kind"])
+    if kind == "elliptic_zoh":
+        A, B = G.elliptic_stage_matrices(g["e"], g["theta0"], int(g["N"]), float(g["T"]), int(g["substeps"]))
+    else:
+        A, B = G.cw_stage_matrices(kind, int(g["N"]), float(g["T"]), float(g["nmm"]))
+    assert np.array_equal(A, g["A"]) and np.array_equal(B, g["B"])
