@@ -183,6 +183,8 @@ struct Shard {
     void generate_model(const admmb_generator *gen, int64_t begin, int64_t cnt, int N_, size_t ld_, double *A, double *B,
                         DevBuf<double> &par_e, DevBuf<double> &par_th);
     DevBuf<double> gen_e, gen_th;
+    DevBuf<double> pint_tab;          // parallel-in-time kernel: tables of the current shared factor (iterate_pint.cuh)
+    bool pint_ready = false;
     void run(const admmb_opts *op, admmb_result *res);
     void download(admmb_result *res);
     void shift_warm_start(int k, const double *s0_new_host);
@@ -369,12 +371,13 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
     static const bool p2_default = getenv("ADMMB_P2") ? atoi(getenv("ADMMB_P2")) != 0 : true;
     IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, p2_default, kernel_variant,
-                    rows_zu, device, time_invariant};
+                    rows_zu, device, time_invariant, pint_ready ? pint_tab.p : nullptr};
     last_kernel = KV_THREAD;
     if (FSH && FSMEM) {
         const bool wg = kernel_variant == KV_WG || (kernel_variant == KV_AUTO && wg_takes(P.n_active, iterate_wg_tile_width(c), num_sms));
         const bool tile = kernel_variant == KV_TILE;
-        if (wg && launch_iterate_wg(c, P, adapt)) last_kernel = KV_WG;
+        if (kernel_variant == KV_PINT && launch_iterate_pint(c, P, adapt)) last_kernel = KV_PINT;
+        else if (wg && launch_iterate_wg(c, P, adapt)) last_kernel = KV_WG;
         else if (tile && launch_iterate_res(c, P, adapt)) last_kernel = KV_TILE;
         else launch_iterate_smem(c, P, adapt);
     }
@@ -553,6 +556,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     ++launches;
     CK(cudaGetLastError());
     decoupled = false;
+    pint_ready = false;
     if (fast_pattern && !use_dense && getenv("ADMMB_NO_DECOUPLED") == nullptr) {
         const int64_t nf = shared_factor ? 1 : batch;
         dec_flag.alloc(1);
@@ -568,6 +572,12 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             k_pack_decoupled<<<(unsigned)((nf + 127) / 128), 128, 0, stream>>>(N, nf, shared_factor ? 0 : 1, fac.p, ld, fac_dec.p);
             ++launches;
             CK(cudaGetLastError());
+            if (shared_factor && op->kernel == KV_PINT) {   // opt-in parallel-in-time kernel: tables of this factor
+                pint_tab.alloc(pint_table_size(N));
+                launch_pint_pack(stream, N, fac_dec.p, pint_tab.p);
+                ++launches;
+                pint_ready = true;
+            }
         }
     }
     k_reset<<<gb, 128, 0, stream>>>(batch, ld, rows_zu, z.p, u.p, has_z0 ? z0c.p : nullptr,
@@ -638,8 +648,8 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         int wg_tile = 0;
         {
             IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, false, kernel_variant,
-                            rows_zu, device, time_invariant};
-            if (shared_factor && fsmem) wg_tile = iterate_wg_tile_width(c);
+                            rows_zu, device, time_invariant, nullptr};
+            if (shared_factor && fsmem) wg_tile = kernel_variant == KV_PINT && pint_ready ? iterate_pint_tile_width(c) : iterate_wg_tile_width(c);
         }
         int done_iters = 0;
         while (width > 0 && done_iters < op->max_iter && !(tf32_tail && width <= tail_width)) {
@@ -685,7 +695,8 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             // the working set is repacked only when that drops a pass, and a single-pass working set runs in long launches
             // (a CTA leaves as soon as all its problems are done).
             bool wg_skip = false;
-            if (last_kernel == KV_WG && wg_tile > 0 && cnt[0] > 0 && kernel_variant == KV_AUTO) {
+            if ((last_kernel == KV_WG || last_kernel == KV_PINT) && wg_tile > 0 && cnt[0] > 0 &&
+                (kernel_variant == KV_AUTO || kernel_variant == KV_PINT)) {
                 auto passes = [&](int64_t w) { const int64_t tiles = (w + wg_tile - 1) / wg_tile; return (tiles + num_sms - 1) / num_sms; };
                 const int64_t now = passes(width), then = passes((int64_t)round_up((size_t)cnt[0], 32));
                 wg_skip = then >= now;
@@ -881,7 +892,7 @@ int validate_opts(admmb_ctx *h, const admmb_opts *op)
         return fail(h, ADMMB_E_BADARG, "adaptive rho needs mu > 1, tau > 1, every >= 1");
     if (op->xupdate < 0 || op->xupdate > 2) return fail(h, ADMMB_E_BADARG, "xupdate must be an ADMMB_XUPDATE_* code");
     if (op->precision != ADMMB_PREC_FP64 && op->precision != ADMMB_PREC_TF32) return fail(h, ADMMB_E_BADARG, "bad precision");
-    if (op->kernel < ADMMB_KERNEL_AUTO || op->kernel > ADMMB_KERNEL_WG) return fail(h, ADMMB_E_BADARG, "kernel must be an ADMMB_KERNEL_* code");
+    if (op->kernel < ADMMB_KERNEL_AUTO || op->kernel > ADMMB_KERNEL_PINT) return fail(h, ADMMB_E_BADARG, "kernel must be an ADMMB_KERNEL_* code");
     // TF32 + dense: the tensor-core path throughout; TF32 + auto: tensor cores are allowed where they are faster
     // (narrow working sets, eligible problems; otherwise the FP64 Riccati kernel runs)
     if (op->precision == ADMMB_PREC_TF32 && op->xupdate == ADMMB_XUPDATE_RICCATI)

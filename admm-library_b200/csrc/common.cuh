@@ -27,7 +27,7 @@ constexpr int PAR_LAM = 0, PAR_RAD = 1, PAR_LO = 2, PAR_HI = 5;
 constexpr int ST_CONVERGED = 0, ST_MAX_ITER = 1, ST_NAN = 2, ST_RUNNING = -1;
 
 // kernel variants of the FP64 Riccati path (include/admm_b200.h ADMMB_KERNEL_*)
-constexpr int KV_AUTO = 0, KV_THREAD = 1, KV_THREAD_WIDE = 2, KV_THREAD2 = 3, KV_TILE = 4, KV_WG = 5;
+constexpr int KV_AUTO = 0, KV_THREAD = 1, KV_THREAD_WIDE = 2, KV_THREAD2 = 3, KV_TILE = 4, KV_WG = 5, KV_PINT = 6;
 
 constexpr int NUM_SMS_B200 = 148;
 constexpr double RHO_MAX = 1.0e6, RHO_MIN = 1.0e-6;   // adaptive rho never leaves this range

@@ -12,6 +12,7 @@ struct IterLaunchCtx {
     int rows_zu;                  // rows of the compact z / u arrays
     int device;
     bool time_invariant;          // shared model whose A_k, B_k are the same for every stage (bitwise)
+    const double *pint_table;     // parallel-in-time kernel: correction / transition tables of the current factor (or null)
 };
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
@@ -26,4 +27,10 @@ bool iterate_res_eligible(const IterLaunchCtx &c);
 // shared factor, the fast block pattern, no affine term / linear cost / per-problem parameters)
 bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 int iterate_wg_tile_width(const IterLaunchCtx &c);
+// parallel-in-time kernel (iterate_pint.cuh): eight warps sweep eight chunks of stages at the same time;
+// same eligibility as the warp-group kernel; FP64 but not the oracle's operation order, hence opt-in (KV_PINT) only
+bool launch_iterate_pint(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+int iterate_pint_tile_width(const IterLaunchCtx &c);
+size_t pint_table_size(int N);
+void launch_pint_pack(cudaStream_t stream, int N, const double *fac_dec, double *table);
 }  // namespace admmb

@@ -17,7 +17,7 @@ XUPDATE = {"auto": 0, "dense": 1, "riccati": 2}
 # "auto" once the working set is narrow); tf32_single: unit entry point only
 PRECISION = {"fp64": 0, "tf32": 1, "tf32_single": 2}
 # kernel variant of the FP64 Riccati path (include/admm_b200.h ADMMB_KERNEL_*): "auto" in normal use
-KERNEL = {"auto": 0, "thread": 1, "thread_wide": 2, "thread2": 3, "tile": 4, "wg": 5}
+KERNEL = {"auto": 0, "thread": 1, "thread_wide": 2, "thread2": 3, "tile": 4, "wg": 5, "pint": 6}
 DEFAULT_KERNEL = "auto"   # what make_opts uses when opts has no "kernel" key (the GPU test suite pins each variant in turn)
 FS = 156  # doubles per stage in a factor record (csrc/common.cuh)
 # name -> (offset, rows, cols, row stride) inside one record

@@ -77,7 +77,11 @@ enum {
     ADMMB_KERNEL_THREAD_WIDE = 2,  /* one problem per thread, uncapped registers, deeper prefetch            */
     ADMMB_KERNEL_THREAD2 = 3,      /* two problems per thread (full-width working sets)                      */
     ADMMB_KERNEL_TILE = 4,         /* resident tile: one warp per 32 problems, iterates in shared memory     */
-    ADMMB_KERNEL_WG = 5            /* warp group: four role-split warps per 32-problem resident tile         */
+    ADMMB_KERNEL_WG = 5,           /* warp group: eight role-split warps per 32-problem resident tile        */
+    ADMMB_KERNEL_PINT = 6          /* parallel in time: eight warps sweep eight chunks of stages at the
+                                      same time, chunk boundaries by superposition.  FP64, but not the oracle's operation
+                                      order: x, z, u agree with it to ~1e-12 relative, iteration counts to +-1 on threshold
+                                      cases.  OPT-IN only: AUTO never picks it (the default path is bit-exact)          */
 };
 
 typedef struct admmb_ctx *admmb_handle;

@@ -583,3 +583,79 @@ def test_generator_bad_arguments(solver, pkg, P):
         with pytest.raises(pkg._lib.AdmmError) as ei:
             solver.solve_generated(gp, gen, opts)
         assert ei.value.code == pkg._lib.E_BADARG
+
+
+# ---- parallel-in-time kernel: opts.kernel = "pint" -----------------------------------------------------
+# FP64, but not the oracle's operation order (chunked sweeps joined by superposition, norms summed per chunk first), so
+# the bar is the north_star's: x, z, u within 1e-9 relative, same iteration count at convergence.  A problem whose
+# residual sits within rounding of its threshold may stop one iteration apart; the tests allow that on at most 1 % of
+# the problems (none observed on these seeds) and compare the iterates of the others.
+PINT_TOL = 1e-9
+
+
+def assert_pint_matches(got, ref, what):
+    ig, ir = got[3]["iters"].astype(np.int64), ref[3]["iters"].astype(np.int64)
+    eq = ig == ir
+    assert np.abs(ig - ir).max() <= 1, f"{what}: iteration counts differ by more than one"
+    assert eq.mean() >= 0.99, f"{what}: {int((~eq).sum())} of {len(eq)} iteration counts differ"
+    assert np.array_equal(got[3]["status"][eq], ref[3]["status"][eq]), f"{what}: statuses differ"
+    for a, b, name in zip(got[:3], ref[:3], "xzu"):
+        scale = max(1.0, np.abs(b[eq]).max())
+        assert np.abs(a[eq] - b[eq]).max() <= PINT_TOL * scale, f"{what}: {name} differs by {np.abs(a[eq] - b[eq]).max():.2e}"
+    for k in ("r_norm", "s_norm", "eps_pri", "eps_dual", "rho"):
+        # (residuals of a problem converged down to rounding level are themselves rounding noise: absolute floor)
+        assert np.allclose(got[3][k][eq], ref[3][k][eq], rtol=1e-6, atol=1e-10), f"{what}: final {k} differs"
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 8, 9, 20, 50])
+def test_pint_kernel_matches_oracle_over_horizons(solver, cpu_oracle, P, N):
+    """Every chunking: fewer stages than warps (N < 8), one stage per warp, ragged chunks (N = 9, 20, 50)."""
+    prob, opts = P.cfg2_cw_batch(batch=97, N=N, seed=10 + N)
+    opts = dict(opts, max_iter=3000)
+    assert_pint_matches(solver.solve(prob, dict(opts, kernel="pint")), cpu_oracle.solve(prob, opts), f"pint cfg2 N={N}")
+
+
+@pytest.mark.parametrize("batch", [1, 31, 33, 257])
+def test_pint_kernel_ragged_batches_and_short_launches(solver, cpu_oracle, P, batch):
+    prob, opts = P.cfg2_cw_batch(batch=batch, N=20, seed=3)
+    opts = dict(opts, max_iter=2500)
+    ref = cpu_oracle.solve(prob, opts)
+    assert_pint_matches(solver.solve(prob, dict(opts, kernel="pint")), ref, f"pint batch={batch}")
+    assert_pint_matches(solver.solve(prob, dict(opts, kernel="pint", chunk=7)), ref, f"pint batch={batch}, 7-iteration launches")
+
+
+def test_pint_kernel_soc_adaptive_history_and_generated_model(solver, cpu_oracle, P):
+    from oracle import gen_ocp as G
+    prob, opts = P.cfg3_lowthrust_soc(batch=130, N=40, seed=5)            # SOC prox, zero-order-hold B
+    opts = dict(opts, max_iter=3000)
+    assert_pint_matches(solver.solve(prob, dict(opts, kernel="pint")), cpu_oracle.solve(prob, opts), "pint cfg3")
+    prob, opts = P.cfg5_montecarlo(batch=200, N=20, seed=6)               # adaptive rho: dual rescaling inside the launch
+    opts = dict(opts, max_iter=4000, adapt_every=10, adapt_until=200, adapt_mu=5.0)
+    assert_pint_matches(solver.solve(prob, dict(opts, kernel="pint")), cpu_oracle.solve(prob, opts), "pint cfg5 adaptive")
+    prob, opts = P.cfg1_single_impulsive()                                # residual history
+    opts = dict(opts, max_iter=3000, history=1)
+    got, ref = solver.solve(prob, dict(opts, kernel="pint")), cpu_oracle.solve(prob, opts)
+    assert_pint_matches(got, ref, "pint cfg1")
+    assert np.allclose(got[3]["hist"]["r_norm"], ref[3]["hist"]["r_norm"], rtol=1e-6, atol=1e-10, equal_nan=True)
+    prob, opts = P.cfg2_cw_batch(batch=64, N=16, seed=43)                 # model generated on the device
+    A, B = G.cw_stage_matrices("cw_impulsive", 16, 2 * np.pi / 16)
+    gp = {k: v for k, v in prob.items() if k not in ("A", "B")}
+    gp["N"] = 16
+    got = solver.solve_generated(gp, dict(kind="cw_impulsive", T=2 * np.pi / 16), dict(opts, max_iter=500, kernel="pint"))
+    assert_pint_matches(got, cpu_oracle.solve(dict(prob, A=A, B=B), dict(opts, max_iter=500)), "pint generated")
+
+
+def test_pint_kernel_multi_tile_benchmark_shape(solver, cpu_oracle, P):
+    """More tiles than SMs (two passes per CTA), N = 50, fixed 300 iterations + repacking to tolerance on a slice."""
+    prob, opts = P.cfg2_cw_batch(batch=6000, N=50, seed=77)
+    o = dict(opts, max_iter=300)
+    assert_pint_matches(solver.solve(prob, dict(o, kernel="pint")), cpu_oracle.solve(prob, o), "pint 6000 x 50")
+    sl = {k: (v[:512] if isinstance(v, np.ndarray) and v.shape[0] == 6000 else v) for k, v in prob.items()}
+    assert_pint_matches(solver.solve(sl, dict(opts, kernel="pint")), cpu_oracle.solve(sl, opts), "pint 512 x 50 to tolerance")
+
+
+def test_pint_kernel_falls_back_when_not_applicable(solver, cpu_oracle, P):
+    """Per-problem models / quadratic cost: the pinned variant does not apply and the automatic (bit-exact) choice runs."""
+    prob, opts = P.lqr_tracking(batch=40, N=10, seed=2)
+    opts = dict(opts, max_iter=150)
+    assert_bit_identical(solver.solve(prob, dict(opts, kernel="pint")), cpu_oracle.solve(prob, opts), "pint fallback lqr")
