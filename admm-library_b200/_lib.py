@@ -19,7 +19,7 @@ EXPORTS = ["admmb_version", "admmb_create", "admmb_destroy", "admmb_last_error",
            "admmb_solve", "admmb_upload", "admmb_run", "admmb_download", "admmb_set_stream", "admmb_shift_resolve",
            "admmb_k_riccati_factor", "admmb_k_xupdate_riccati", "admmb_k_prox_dual_residuals",
            "admmb_k_dense_factor", "admmb_k_xupdate_dense",
-           "admmb_upload_generated", "admmb_solve_generated", "admmb_k_generate"]
+           "admmb_upload_generated", "admmb_solve_generated", "admmb_k_generate", "admmb_nccl_gathers"]
 
 
 class Problem(C.Structure):
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.admmb_last_error.argtypes = [H]
     L.admmb_last_error.restype = C.c_char_p
     L.admmb_device_count.argtypes = [H]
+    L.admmb_nccl_gathers.argtypes = [H]
     L.admmb_solve.argtypes = [H, C.POINTER(Problem), C.POINTER(Opts), C.POINTER(Result)]
     L.admmb_upload.argtypes = [H, C.POINTER(Problem), C.POINTER(Opts)]
     L.admmb_run.argtypes = [H, C.POINTER(Opts), C.POINTER(Result)]

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <dlfcn.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -801,8 +802,49 @@ void Shard::download(admmb_result *res)
 // ------------------------------------------------------------------------------------------------
 // the handle
 // ------------------------------------------------------------------------------------------------
+// The final statistics gather of a multi-GPU handle: one NCCL all-reduce of four 64-bit integers per GPU --
+// {converged, sum of iterations, refactorisations} summed, {max iterations} maximised -- over NVLink; the only bytes of
+// a solve that cross between GPUs.  libnccl is opened at run time (dlopen: the library has no link-time dependency on
+// it); where it is absent the same four integers are summed on the host.
+struct NcclApi {
+    typedef struct ncclComm *comm_t;
+    void *lib = nullptr;
+    int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    static constexpr int kInt64 = 4, kSum = 0, kMax = 2;      // ncclInt64, ncclSum, ncclMax (nccl.h, stable since NCCL 2.0)
+    bool open()
+    {
+        if (lib) return true;
+        if (getenv("ADMMB_NO_NCCL")) return false;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd && GetErrorString) return true;
+        dlclose(lib);
+        lib = nullptr;
+        return false;
+    }
+};
+
 struct admmb_ctx {
     std::vector<Shard> shards;
+    NcclApi nccl;
+    std::vector<NcclApi::comm_t> comms;      // one communicator per shard (ncclCommInitAll), created at the first gather
+    int nccl_state = 0;                      // 0: not tried, 1: communicators ready, -1: unavailable (host sum)
+    std::vector<DevBuf<long long>> stat_buf; // per shard: [0..3] send {conv, iters, refac, 0}, [4] send max, [5..8] recv, [9] recv max
+    int64_t stat_gathers = 0;                // all-reduces done (tests)
     std::string err;
     std::mutex mu;
     bool uploaded = false;
@@ -931,6 +973,45 @@ void for_each_shard(admmb_ctx *h, Fn fn)
         if (errs[g].e != cudaSuccess) throw errs[g];
 }
 
+// the statistics of a multi-GPU solve, all-reduced over NCCL straight from each GPU's device counters
+// ([0] refactorisations, [1] converged, [2] sum of iterations, [3] max iterations -- k_stats).  *done stays false when
+// libnccl cannot be opened (the caller then sums the per-GPU results on the host); a failing NCCL call is ADMMB_E_NCCL.
+int nccl_gather(admmb_ctx *h, int64_t out[4], bool *done)
+{
+    *done = false;
+    const int G = (int)h->shards.size();
+    if (G < 2 || h->nccl_state < 0) return ADMMB_OK;
+    NcclApi &N = h->nccl;
+    if (h->nccl_state == 0) {
+        if (!N.open()) { h->nccl_state = -1; return ADMMB_OK; }
+        std::vector<int> devs(G);
+        for (int g = 0; g < G; ++g) devs[g] = h->shards[g].device;
+        h->comms.assign(G, nullptr);
+        const int rc = N.CommInitAll(h->comms.data(), G, devs.data());
+        if (rc != 0) { h->nccl_state = -1; h->comms.clear(); return fail(h, ADMMB_E_NCCL, "ncclCommInitAll: %s", N.GetErrorString(rc)); }
+        h->stat_buf.resize(G);
+        for (int g = 0; g < G; ++g) { CK(cudaSetDevice(h->shards[g].device)); h->stat_buf[g].alloc(5); }
+        h->nccl_state = 1;
+    }
+    int rc = N.GroupStart();
+    for (int g = 0; g < G && rc == 0; ++g) {
+        Shard &s = h->shards[g];
+        CK(cudaSetDevice(s.device));
+        rc = N.AllReduce(s.counters.p, h->stat_buf[g].p, 4, NcclApi::kInt64, NcclApi::kSum, h->comms[g], s.stream);
+        if (rc == 0) rc = N.AllReduce(s.counters.p + 3, h->stat_buf[g].p + 4, 1, NcclApi::kInt64, NcclApi::kMax, h->comms[g], s.stream);
+    }
+    const int rc2 = N.GroupEnd();
+    if (rc != 0 || rc2 != 0) return fail(h, ADMMB_E_NCCL, "ncclAllReduce: %s", N.GetErrorString(rc != 0 ? rc : rc2));
+    long long hv[5];
+    CK(cudaSetDevice(h->shards[0].device));
+    CK(cudaMemcpyAsync(hv, h->stat_buf[0].p, sizeof(hv), cudaMemcpyDeviceToHost, h->shards[0].stream));
+    for (int g = 0; g < G; ++g) { CK(cudaSetDevice(h->shards[g].device)); CK(cudaStreamSynchronize(h->shards[g].stream)); }
+    out[0] = hv[1]; out[1] = hv[2]; out[2] = hv[4]; out[3] = hv[0];
+    ++h->stat_gathers;
+    *done = true;
+    return ADMMB_OK;
+}
+
 void shard_range(int64_t batch, int G, int g, int64_t &begin, int64_t &cnt)
 {
     const int64_t per = (batch + G - 1) / G;
@@ -980,6 +1061,9 @@ int admmb_destroy(admmb_handle h)
         cudaSetDevice(s.device);
         cudaStreamSynchronize(s.stream);
     }
+    for (auto c : h->comms)
+        if (c && h->nccl.CommDestroy) h->nccl.CommDestroy(c);
+    h->comms.clear();
     for (auto &s : h->shards) s.destroy();
     delete h;   // DevBuf destructors release the device memory (cudaFree is device-agnostic under UVA)
     return ADMMB_OK;
@@ -988,6 +1072,8 @@ int admmb_destroy(admmb_handle h)
 const char *admmb_last_error(admmb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int admmb_device_count(admmb_handle h) { return h ? (int)h->shards.size() : 0; }
+
+int admmb_nccl_gathers(admmb_handle h) { return h ? (int)h->stat_gathers : 0; }
 
 int admmb_set_stream(admmb_handle h, void *cuda_stream)
 {
@@ -1054,6 +1140,11 @@ int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
             Shard &s = h->shards[g];
             memset(&part[g], 0, sizeof(admmb_result));
             if (s.batch > 0 && s.uploaded) s.run(op, &part[g]);
+            else if (h->shards.size() > 1) {       // a GPU without problems still takes part in the statistics all-reduce
+                CK(cudaSetDevice(s.device));
+                s.counters.alloc(4);
+                CK(cudaMemsetAsync(s.counters.p, 0, sizeof(unsigned long long) * 4, s.stream));
+            }
         });
         return (int)ADMMB_OK;
     });
@@ -1075,6 +1166,18 @@ int admmb_run(admmb_handle h, const admmb_opts *op, admmb_result *res)
             res->stats[3] += part[g].stats[3];
             res->device_ms = std::max(res->device_ms, part[g].device_ms);
             res->launches += h->shards[g].launches;
+        }
+        // several GPUs in this process: the same totals by one NCCL all-reduce over NVLink (4 + 1 integers per GPU), read
+        // back from GPU 0; they must agree with the host-side sums above
+        int64_t tot[4];
+        bool done = false;
+        int rcn = guarded(h, [&]() { return nccl_gather(h, tot, &done); });
+        if (rcn != ADMMB_OK) return rcn;
+        if (done) {
+            for (int i = 0; i < 4; ++i)
+                if (tot[i] != res->stats[i])
+                    return fail(h, ADMMB_E_NCCL, "statistics all-reduce disagrees with the per-GPU sums (field %d: %lld vs %lld)", i,
+                                (long long)tot[i], (long long)res->stats[i]);
         }
     }
     return ADMMB_OK;

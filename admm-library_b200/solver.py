@@ -190,6 +190,11 @@ class Solver:
     def device_count(self) -> int:
         return int(self._L.admmb_device_count(self._h))
 
+    @property
+    def nccl_gathers(self) -> int:
+        """Statistics all-reduces done over NCCL by this (multi-GPU) handle; 0: one GPU or libnccl not found."""
+        return int(self._L.admmb_nccl_gathers(self._h))
+
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._L.admmb_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 

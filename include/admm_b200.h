@@ -40,7 +40,7 @@ enum {
     ADMMB_OK = 0,
     ADMMB_E_BADARG = -1,
     ADMMB_E_CUDA = -2,
-    ADMMB_E_NCCL = -3,
+    ADMMB_E_NCCL = -3,      /* a call of the statistics all-reduce failed (multi-GPU handles only) */
     ADMMB_E_NOMEM = -4,
     ADMMB_E_NODEVICE = -5,
     ADMMB_E_STATE = -6      /* staged API called out of order */
@@ -148,6 +148,9 @@ int admmb_create(admmb_handle *out, const int *device_ids, int n_devices);
 int admmb_destroy(admmb_handle h);
 const char *admmb_last_error(admmb_handle h);          /* h may be NULL: last create() error   */
 int admmb_device_count(admmb_handle h);
+/* how many statistics all-reduces (result.stats of a multi-GPU handle, 4 + 1 integers per GPU over NCCL /
+ * NVLink, libnccl opened at run time) this handle has done; 0: one GPU, or libnccl not found (host-side sum) */
+int admmb_nccl_gathers(admmb_handle h);
 
 /* ---- the solve (admm_solve) --------------------------------------------- */
 /* upload + run + download in one blocking call; shards `batch` contiguously over the handle's GPUs. */

@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the canonical-order
 C oracle on the same seeded inputs.  Bar: FP64 results bit-identical (iteration counts, x, z, u,
 residual history) -- stricter than the 1e-9 relative the north_star asks for."""
+import os
+
 import numpy as np
 import pytest
 
@@ -202,6 +204,14 @@ def test_two_gpus_in_one_process_match_one_gpu(pkg, cpu_oracle, P):
     opts = dict(opts, max_iter=400)
     got = s2.solve(prob, opts)
     assert s2.device_count == 2
+    # the statistics come out of one NCCL all-reduce over the two GPUs' device counters (libnccl opened at run
+    # time; the library cross-checks it against the per-GPU sums and returns ADMMB_E_NCCL on a mismatch)
+    import ctypes.util
+    if ctypes.util.find_library("nccl") or any(os.path.exists(p) for p in ("/usr/lib/x86_64-linux-gnu/libnccl.so.2",)):
+        assert s2.nccl_gathers >= 1
+    small, _ = P.cfg2_cw_batch(batch=1, N=12, seed=13)       # fewer problems than GPUs: the idle GPU still takes part
+    g1 = s2.solve(small, opts)
+    assert g1[3]["stats"][0] + 0 == int((g1[3]["status"] == 0).sum())
     s2.close()
     ref = cpu_oracle.solve(prob, opts)
     assert_bit_identical(got, ref, "two GPUs, one process")
