@@ -19,7 +19,8 @@ EXPORTS = ["admmb_version", "admmb_create", "admmb_destroy", "admmb_last_error",
            "admmb_solve", "admmb_upload", "admmb_run", "admmb_download", "admmb_set_stream", "admmb_shift_resolve",
            "admmb_k_riccati_factor", "admmb_k_xupdate_riccati", "admmb_k_prox_dual_residuals",
            "admmb_k_dense_factor", "admmb_k_xupdate_dense",
-           "admmb_upload_generated", "admmb_solve_generated", "admmb_k_generate", "admmb_nccl_gathers"]
+           "admmb_upload_generated", "admmb_solve_generated", "admmb_k_generate", "admmb_nccl_gathers",
+           "admmb_scp_solve", "admmb_k_scp_linearise"]
 
 
 class Problem(C.Structure):
@@ -32,6 +33,16 @@ class Problem(C.Structure):
 class Generator(C.Structure):
     _fields_ = [("kind", C.c_int32), ("substeps", C.c_int32), ("T", C.c_double), ("nmm", C.c_double),
                 ("e", c_dp), ("theta0", c_dp)]
+
+
+class Scp(C.Structure):
+    _fields_ = [("model", C.c_int32), ("substeps", C.c_int32), ("T", C.c_double), ("nmm", C.c_double),
+                ("R0", C.c_double), ("max_pass", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double)]
+
+
+class ScpResult(C.Structure):
+    _fields_ = [("passes", c_ip), ("scp_status", c_ip), ("step", c_dp), ("iters_total", C.POINTER(C.c_int64)),
+                ("hist_step", c_dp), ("stats", C.c_int64 * 4), ("linearise_ms", C.c_double)]
 
 
 class Opts(C.Structure):
@@ -92,6 +103,9 @@ def load() -> C.CDLL:
     L.admmb_upload_generated.argtypes = [H, C.POINTER(Problem), C.POINTER(Generator), C.POINTER(Opts)]
     L.admmb_solve_generated.argtypes = [H, C.POINTER(Problem), C.POINTER(Generator), C.POINTER(Opts), C.POINTER(Result)]
     L.admmb_k_generate.argtypes = [H, C.c_int32, C.c_int64, C.POINTER(Generator), c_dp, c_dp]
+    L.admmb_scp_solve.argtypes = [H, C.POINTER(Problem), C.POINTER(Scp), C.POINTER(Opts), C.POINTER(Result),
+                                  C.POINTER(ScpResult)]
+    L.admmb_k_scp_linearise.argtypes = [H, C.c_int32, C.c_int64, C.POINTER(Scp), C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp]
     for name in EXPORTS:
         if name not in ("admmb_last_error",):
             getattr(L, name).restype = C.c_int

@@ -25,6 +25,7 @@
 #include "iterate_launch_decl.cuh"
 #include "dense.cuh"
 #include "generators.cuh"
+#include "scp.cuh"
 
 using namespace admmb;
 
@@ -189,6 +190,17 @@ struct Shard {
     void run(const admmb_opts *op, admmb_result *res);
     void download(admmb_result *res);
     void shift_warm_start(int k, const double *s0_new_host);
+    // sequential convex programming on the resident batch (scp.cuh)
+    bool scp_upload = false;          // set around upload(): per-problem model + affine term, produced on the device
+    const int *run_active = nullptr;  // run(): problems with a zero entry keep the state of their last solve
+    DevBuf<double> scp_xref, scp_step, scp_hist;
+    DevBuf<int> scp_active, scp_passes, scp_status, scp_count;
+    DevBuf<long long> scp_iters;
+    int scp_max_pass = 0;
+    double scp_lin_ms = 0.0;
+    void scp_linearise(const ScpConst &C, bool shoot);
+    void scp_solve(const admmb_scp *sc, const admmb_opts *op, admmb_result *res);
+    void scp_download(admmb_scp_result *out);
     template <bool FSH, bool FSMEM>
     void launch_iterate(const IterParams &P, bool adapt);
 };
@@ -223,8 +235,8 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     batch = cnt;
     p_begin = begin;
     ld = round_up((size_t)cnt, 32);
-    dyn_batched = gen ? gen->kind == GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0;
-    has_c = pb->c != nullptr;
+    dyn_batched = scp_upload ? true : (gen ? gen->kind == GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0);
+    has_c = scp_upload || pb->c != nullptr;
     has_Q = pb->Q != nullptr;
     has_R = pb->R != nullptr;
     has_q = pb->q != nullptr;
@@ -276,7 +288,7 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
     }
 
     time_invariant = !dyn_batched;
-    for (int k = 1; k < N && time_invariant && !gen; ++k)
+    for (int k = 1; k < N && time_invariant && !gen && !scp_upload; ++k)
         time_invariant = memcmp(pb->A, pb->A + (size_t)36 * k, 36 * sizeof(double)) == 0 &&
                          memcmp(pb->B, pb->B + (size_t)18 * k, 18 * sizeof(double)) == 0;
 
@@ -288,7 +300,14 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
         if (dyn_batched) upload_rows(host + (size_t)begin * R, cnt, R, buf.p, nullptr);
         else CK(cudaMemcpyAsync(buf.p, host, sizeof(double) * R, cudaMemcpyHostToDevice, stream));
     };
-    if (gen) {
+    if (scp_upload) {   // the linearisation kernels fill these each pass
+        rawA.alloc((size_t)36 * N * md);
+        rawB.alloc((size_t)18 * N * md);
+        rawc.alloc((size_t)6 * N * md);
+        CK(cudaMemsetAsync(rawA.p, 0, sizeof(double) * 36 * N * md, stream));
+        CK(cudaMemsetAsync(rawB.p, 0, sizeof(double) * 18 * N * md, stream));
+        CK(cudaMemsetAsync(rawc.p, 0, sizeof(double) * 6 * N * md, stream));
+    } else if (gen) {
         rawA.alloc((size_t)36 * N * md);
         rawB.alloc((size_t)18 * N * md);
         if (dyn_batched) {   // columns beyond the batch stay finite
@@ -300,7 +319,7 @@ void Shard::upload(const admmb_problem *pb, const admmb_opts *op, int64_t begin,
         up_model(rawA, pb->A, 36 * N);
         up_model(rawB, pb->B, 18 * N);
     }
-    up_model(rawc, pb->c, 6 * N);
+    if (!scp_upload) up_model(rawc, pb->c, 6 * N);
     up_model(rawQ, pb->Q, 36 * (N + 1));
     up_model(rawR, pb->R, 9 * N);
 
@@ -512,6 +531,135 @@ void Shard::shift_warm_start(int k, const double *s0_new_host)
     CK(cudaStreamSynchronize(stream));       // `src` and the staging buffer are reused by the caller
 }
 
+// ------------------------------------------------------------------------------------------------
+// sequential convex programming on the resident batch (kernels: scp.cuh, oracle: oracle/scp_ocp.py)
+// ------------------------------------------------------------------------------------------------
+void Shard::scp_linearise(const ScpConst &C, bool shoot)
+{
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, stream));
+    const unsigned gb = (unsigned)((batch + 127) / 128);
+    if (shoot) {
+        k_scp_shoot<<<gb, 128, 0, stream>>>(C, batch, N, ld, s0.p, scp_xref.p, rawA.p, rawB.p, rawc.p);
+    } else {
+        dim3 grid(gb, (unsigned)N);
+        k_scp_linearise<<<grid, 128, 0, stream>>>(C, batch, N, ld, scp_active.p, scp_xref.p, rawA.p, rawB.p, rawc.p);
+    }
+    ++launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(b, stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (e != cudaSuccess) throw CudaFail{e, "scp_linearise"};
+    scp_lin_ms += ms;
+}
+
+void Shard::scp_solve(const admmb_scp *sc, const admmb_opts *op, admmb_result *res)
+{
+    CK(cudaSetDevice(device));
+    ScpConst C;
+    const double nmm = sc->nmm != 0.0 ? sc->nmm : 1.0;
+    C.substeps = sc->substeps > 0 ? sc->substeps : 8;
+    C.R0 = sc->R0;
+    C.twoR0 = 2.0 * sc->R0;
+    C.R0sq = sc->R0 * sc->R0;
+    C.n2 = nmm * nmm;
+    C.tn = 2.0 * nmm;
+    C.dt = sc->T / (double)C.substeps;
+    C.hdt = 0.5 * C.dt;
+    C.dt6 = C.dt / 6.0;
+    scp_max_pass = sc->max_pass;
+    scp_lin_ms = 0.0;
+    scp_xref.alloc((size_t)n * ld);
+    scp_active.alloc(ld);
+    scp_passes.alloc(ld);
+    scp_status.alloc(ld);
+    scp_step.alloc(ld);
+    scp_iters.alloc(ld);
+    scp_hist.alloc((size_t)scp_max_pass * ld);
+    scp_count.alloc(1);
+    xo.alloc((size_t)n * ld);
+    CK(cudaMemsetAsync(scp_xref.p, 0, sizeof(double) * n * ld, stream));           // first reference: free drift (a = 0)
+    CK(cudaMemsetAsync(scp_hist.p, 0xFF, sizeof(double) * (size_t)scp_max_pass * ld, stream));   // NaN after a problem's exit
+    const unsigned gb = (unsigned)((batch + 127) / 128);
+    k_scp_init<<<(unsigned)((ld + 127) / 128), 128, 0, stream>>>(batch, ld, scp_active.p, scp_passes.p, scp_status.p,
+                                                                 scp_step.p, scp_iters.p);
+    ++launches;
+    CK(cudaGetLastError());
+    struct ActiveGuard { Shard &s; ~ActiveGuard() { s.run_active = nullptr; } } guard{*this};
+    auto t0 = std::chrono::steady_clock::now();
+    double kms = 0.0;
+    int64_t kl = 0;
+    for (int pass = 1; pass <= scp_max_pass; ++pass) {
+        scp_linearise(C, pass == 1);
+        if (pass > 1) {   // warm start: the previous pass's (z, u); converged problems are left alone
+            z0c.alloc((size_t)rows_zu * ld);
+            u0c.alloc((size_t)rows_zu * ld);
+            dim3 grid(gb, (unsigned)std::min(rows_zu, 64));
+            k_scp_warm<<<grid, 128, 0, stream>>>(batch, ld, rows_zu, z.p, u.p, usc.p, z0c.p, u0c.p);
+            ++launches;
+            CK(cudaGetLastError());
+            has_z0 = has_u0 = true;
+            run_active = scp_active.p;
+        }
+        admmb_result r;
+        memset(&r, 0, sizeof(r));
+        run(op, &r);
+        kms += r.kernel_ms;
+        kl += r.kernel_launches;
+        k_output<false, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p,
+                                                      nullptr, nullptr);
+        CK(cudaMemsetAsync(scp_count.p, 0, sizeof(int), stream));
+        k_scp_step<<<gb, 128, 0, stream>>>(batch, n, ld, pass, sc->tol_abs, sc->tol_rel, xo.p, scp_xref.p, iters.p,
+                                           scp_active.p, scp_passes.p, scp_status.p, scp_step.p, scp_iters.p, scp_hist.p,
+                                           scp_count.p);
+        launches += 2;
+        CK(cudaGetLastError());
+        int still = 0;
+        CK(cudaMemcpyAsync(&still, scp_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (still == 0) break;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (res) {
+        res->kernel_ms = kms;
+        res->kernel_launches = kl;
+        res->device_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();   // every pass ends with a stream sync
+    }
+    ran = true;
+}
+
+void Shard::scp_download(admmb_scp_result *out)
+{
+    CK(cudaSetDevice(device));
+    const size_t pb = (size_t)p_begin;
+    std::vector<int> hp(batch), hs(batch);
+    std::vector<long long> hi(batch);
+    CK(cudaMemcpyAsync(hp.data(), scp_passes.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hs.data(), scp_status.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hi.data(), scp_iters.p, sizeof(long long) * batch, cudaMemcpyDeviceToHost, stream));
+    if (out->step) CK(cudaMemcpyAsync(out->step + pb, scp_step.p, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int64_t i = 0; i < batch; ++i) {
+        out->stats[0] += hs[i] == 0;
+        out->stats[1] += hi[i];
+        out->stats[2] = std::max<int64_t>(out->stats[2], hp[i]);
+        out->stats[3] += hp[i];
+        if (out->passes) out->passes[pb + i] = hp[i];
+        if (out->scp_status) out->scp_status[pb + i] = hs[i];
+        if (out->iters_total) out->iters_total[pb + i] = hi[i];
+    }
+    if (out->hist_step) {
+        download_rows<double>(scp_hist.p, scp_max_pass, out->hist_step + pb * scp_max_pass, stage);
+        CK(cudaStreamSynchronize(stream));
+    }
+}
+
 __global__ void k_stats(int64_t batch, const int *iters, const int *status, unsigned long long *counters)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,7 +731,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
     }
     k_reset<<<gb, 128, 0, stream>>>(batch, ld, rows_zu, z.p, u.p, has_z0 ? z0c.p : nullptr,
                                     has_u0 ? u0c.p : nullptr, rho.p, has_rho0 ? rho0.p : nullptr, op->rho, usc.p,
-                                    iters.p, status.p, fac_status.p);
+                                    iters.p, status.p, fac_status.p, run_active);
     ++launches;
     CK(cudaGetLastError());
 
@@ -877,7 +1025,7 @@ int cuda_code(cudaError_t e)
 
 int validate_opts(admmb_ctx *h, const admmb_opts *op);
 
-int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op, const admmb_generator *gen = nullptr)
+int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op, const admmb_generator *gen = nullptr, bool scp = false)
 {
     if (!pb || !op) return fail(h, ADMMB_E_BADARG, "null problem/opts");
     if (gen) {
@@ -896,9 +1044,9 @@ int validate(admmb_ctx *h, const admmb_problem *pb, const admmb_opts *op, const 
     }
     if (pb->N < 1 || pb->N > 4096) return fail(h, ADMMB_E_BADARG, "N out of range");
     if (pb->batch < 1 || pb->batch > (int64_t)1 << 30) return fail(h, ADMMB_E_BADARG, "batch out of range");
-    if ((!gen && (!pb->A || !pb->B)) || !pb->s0 || !pb->block_type || !pb->block_par)
+    if ((!gen && !scp && (!pb->A || !pb->B)) || !pb->s0 || !pb->block_type || !pb->block_par)
         return fail(h, ADMMB_E_BADARG, "A, B, s0, block_type and block_par are required");
-    const bool model_batched = gen ? gen->kind == ADMMB_GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0;
+    const bool model_batched = scp || (gen ? gen->kind == ADMMB_GEN_ELLIPTIC_ZOH : pb->dyn_batched != 0);
     const int nb = 3 * pb->N + 2;
     int nsplit = 0;
     for (int b = 0; b < nb; ++b) {
@@ -1204,6 +1352,86 @@ int admmb_shift_resolve(admmb_handle h, int32_t k, const double *s0_new, const a
         if (rc != ADMMB_OK) return rc;
     }
     return admmb_run(h, op, res);
+}
+
+int admmb_scp_solve(admmb_handle h, const admmb_problem *pb, const admmb_scp *sc, const admmb_opts *op, admmb_result *res,
+                    admmb_scp_result *out)
+{
+    if (!h || !res) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->uploaded = false;
+    int rc = validate(h, pb, op, nullptr, true);
+    if (rc != ADMMB_OK) return rc;
+    if (!sc) return fail(h, ADMMB_E_BADARG, "null scp");
+    if (sc->model != ADMMB_SCP_NL_CIRCULAR) return fail(h, ADMMB_E_BADARG, "scp: model must be an ADMMB_SCP_* code");
+    if (!(sc->T > 0.0) || !std::isfinite(sc->T)) return fail(h, ADMMB_E_BADARG, "scp: stage length T must be > 0");
+    if (!(sc->R0 > 0.0) || !std::isfinite(sc->R0)) return fail(h, ADMMB_E_BADARG, "scp: orbit radius R0 must be > 0");
+    if (!(sc->nmm >= 0.0) || !std::isfinite(sc->nmm)) return fail(h, ADMMB_E_BADARG, "scp: mean motion must be > 0 (0 = 1)");
+    if (sc->substeps < 0 || sc->substeps > 4096) return fail(h, ADMMB_E_BADARG, "scp: substeps out of range");
+    if (sc->max_pass < 1 || sc->max_pass > 1000) return fail(h, ADMMB_E_BADARG, "scp: max_pass must be in 1 .. 1000");
+    if (!(sc->tol_abs >= 0.0) || !(sc->tol_rel >= 0.0)) return fail(h, ADMMB_E_BADARG, "scp: tolerances must be >= 0");
+    if (op->adapt_rho || op->history || pb->rho0)
+        return fail(h, ADMMB_E_BADARG, "scp: adaptive / per-problem rho and the per-iteration history are not carried across passes");
+    if (op->xupdate == ADMMB_XUPDATE_DENSE || op->precision != ADMMB_PREC_FP64)
+        return fail(h, ADMMB_E_BADARG, "scp: per-problem linearisations need the FP64 Riccati path (xupdate = auto / riccati)");
+    for (auto &s : h->shards) s.launches = 0;
+    const int G = (int)std::min<int64_t>((int64_t)h->shards.size(), pb->batch);
+    std::vector<admmb_result> part(h->shards.size());
+    auto t0 = std::chrono::steady_clock::now();
+    std::chrono::steady_clock::time_point t1, t2;
+    rc = guarded(h, [&]() {
+        for_each_shard(h, [&](int g) {
+            int64_t b, c;
+            shard_range(pb->batch, G, g, b, c);
+            Shard &s = h->shards[g];
+            memset(&part[g], 0, sizeof(admmb_result));
+            if (g >= G || c <= 0) { s.uploaded = false; s.batch = 0; return; }
+            struct Flag { bool &f; ~Flag() { f = false; } } flag{s.scp_upload};
+            s.scp_upload = true;
+            s.upload(pb, op, b, c, nullptr);
+        });
+        t1 = std::chrono::steady_clock::now();
+        for_each_shard(h, [&](int g) {
+            Shard &s = h->shards[g];
+            if (s.batch > 0 && s.uploaded) s.scp_solve(sc, op, &part[g]);
+        });
+        t2 = std::chrono::steady_clock::now();
+        admmb_scp_result tmp;
+        memset(&tmp, 0, sizeof(tmp));
+        admmb_scp_result *o = out ? out : &tmp;
+        o->stats[0] = o->stats[1] = o->stats[2] = o->stats[3] = 0;
+        o->linearise_ms = 0.0;
+        // the shards write disjoint ranges of the caller's buffers; the small statistics are summed here
+        for (auto &s : h->shards) {
+            if (!(s.batch > 0 && s.uploaded)) continue;
+            s.download(res);
+            s.scp_download(o);
+            o->linearise_ms = std::max(o->linearise_ms, s.scp_lin_ms);
+        }
+        res->stats[0] = res->stats[1] = res->stats[2] = res->stats[3] = 0;
+        res->device_ms = res->kernel_ms = 0.0;
+        res->launches = res->kernel_launches = 0;
+        for (size_t g = 0; g < part.size(); ++g) {
+            res->device_ms = std::max(res->device_ms, part[g].device_ms);
+            res->kernel_ms = std::max(res->kernel_ms, part[g].kernel_ms);
+            res->kernel_launches += part[g].kernel_launches;
+            res->launches += h->shards[g].launches;
+        }
+        res->stats[0] = o->stats[0];
+        res->stats[1] = o->stats[1];
+        res->stats[2] = o->stats[2];
+        res->stats[3] = 0;
+        return (int)ADMMB_OK;
+    });
+    auto t3 = std::chrono::steady_clock::now();
+    if (rc != ADMMB_OK) return rc;
+    res->h2d_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    res->d2h_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
+    h->uploaded = true;
+    h->batch = pb->batch;
+    h->max_iter = op->max_iter;
+    h->up_opts = *op;
+    return ADMMB_OK;
 }
 
 int admmb_download(admmb_handle h, admmb_result *res)

@@ -1493,10 +1493,13 @@ __global__ void k_iota(int *a, int n)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_reset(int64_t batch, size_t ld, int rows_zu, double *z, double *u, const double *z0,
                         const double *u0, double *rho, const double *rho0, double rho_shared, double *usc,
-                        int *iters, int *status, const int *fac_status)
+                        int *iters, int *status, const int *fac_status, const int *active = nullptr)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
+    // SCP passes (scp.cuh): a problem whose trajectory has converged keeps the state of its last solve -- iterates, iteration
+    // count and a status other than RUNNING, so that no kernel touches it again
+    if (active && !active[p]) return;
     for (int r = 0; r < rows_zu; ++r) {
         z[(size_t)r * ld + p] = z0 ? z0[(size_t)r * ld + p] : 0.0;
         u[(size_t)r * ld + p] = u0 ? u0[(size_t)r * ld + p] : 0.0;

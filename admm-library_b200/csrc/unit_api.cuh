@@ -213,4 +213,39 @@ int admmb_k_generate(admmb_handle h, int32_t N, int64_t batch, const admmb_gener
     });
 }
 
+int admmb_k_scp_linearise(admmb_handle h, int32_t N, int64_t batch, const admmb_scp *sc, int32_t shoot, const double *s0,
+                          double *xref, double *A, double *B, double *c)
+{
+    if (!h || N < 1 || batch < 1 || !sc || !xref || !A || !B || !c || (shoot && !s0)) return ADMMB_E_BADARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (sc->model != ADMMB_SCP_NL_CIRCULAR || !(sc->T > 0.0) || !(sc->R0 > 0.0) || sc->substeps < 0)
+        return fail(h, ADMMB_E_BADARG, "admmb_k_scp_linearise: bad scp parameters");
+    return guarded(h, [&]() {
+        UnitCtx U(h);
+        const size_t ld = round_up((size_t)batch, 32);
+        const int n = 9 * N + 6;
+        DevBuf<double> dA, dB, dc, ds0, dx, stg;
+        dA.alloc((size_t)36 * N * ld);
+        dB.alloc((size_t)18 * N * ld);
+        dc.alloc((size_t)6 * N * ld);
+        U.up_rows(dx, stg, xref, batch, n, ld);
+        if (shoot) U.up_rows(ds0, stg, s0, batch, 6, ld);
+        ScpConst C;
+        const double nmm = sc->nmm != 0.0 ? sc->nmm : 1.0;
+        C.substeps = sc->substeps > 0 ? sc->substeps : 8;
+        C.R0 = sc->R0; C.twoR0 = 2.0 * sc->R0; C.R0sq = sc->R0 * sc->R0;
+        C.n2 = nmm * nmm; C.tn = 2.0 * nmm;
+        C.dt = sc->T / (double)C.substeps; C.hdt = 0.5 * C.dt; C.dt6 = C.dt / 6.0;
+        const unsigned gb = (unsigned)((batch + 127) / 128);
+        if (shoot) k_scp_shoot<<<gb, 128, 0, U.s.stream>>>(C, batch, N, ld, ds0.p, dx.p, dA.p, dB.p, dc.p);
+        else k_scp_linearise<<<dim3(gb, (unsigned)N), 128, 0, U.s.stream>>>(C, batch, N, ld, nullptr, dx.p, dA.p, dB.p, dc.p);
+        CK(cudaGetLastError());
+        U.down_rows(dA.p, stg, A, batch, 36 * N, ld);
+        U.down_rows(dB.p, stg, B, batch, 18 * N, ld);
+        U.down_rows(dc.p, stg, c, batch, 6 * N, ld);
+        if (shoot) U.down_rows(dx.p, stg, xref, batch, n, ld);
+        return (int)ADMMB_OK;
+    });
+}
+
 }  // extern "C"

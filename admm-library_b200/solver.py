@@ -53,6 +53,16 @@ def make_generator(gen: dict):
     return g, (e, th)
 
 
+SCP_MODEL = {"nl_circular": 1}   # include/admm_b200.h ADMMB_SCP_*
+
+
+def make_scp(scp: dict) -> L.Scp:
+    """scp = dict(T=..., R0=..., max_pass=..., tol_abs=..., tol_rel=..., model="nl_circular", nmm=1.0, substeps=8)."""
+    return L.Scp(model=SCP_MODEL[scp.get("model", "nl_circular")], substeps=int(scp.get("substeps", 0)),
+                 T=float(scp["T"]), nmm=float(scp.get("nmm", 0.0)), R0=float(scp["R0"]), max_pass=int(scp["max_pass"]),
+                 tol_abs=float(scp.get("tol_abs", 0.0)), tol_rel=float(scp.get("tol_rel", 0.0)))
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(L.c_dp)
 
@@ -219,6 +229,44 @@ class Solver:
         g, keep = make_generator(gen)
         self._check(self._L.admmb_solve_generated(self._h, C.byref(pb), C.byref(g), C.byref(op), C.byref(res.c)))
         return res.x, res.z, res.u, res.hist_dict()
+
+    def scp_solve(self, prob: dict, scp: dict, opts: dict, want=("x", "z", "u")):
+        """Sequential convex programming on the device (oracle/scp_ocp.py scp_solve): prob carries N, s0,
+        the block table and optionally q / per-problem Q, R -- the stage records are re-linearised on the GPU each pass.
+        -> x, z, u, info (hist_dict of the last convex solves + passes, scp_status, step, iters_total, hist_step)."""
+        m = to_c_layout(dict(prob, A=None, B=None, c=None))
+        n = 9 * m["N"] + 6
+        Bsz = m["batch"]
+        op = make_opts(opts)
+        sc = make_scp(scp)
+        res = ResultBuffers(Bsz, n, op.max_iter, False, want)
+        pb = make_problem(m)
+        passes = np.zeros(Bsz, dtype=np.int32)
+        scp_status = np.zeros(Bsz, dtype=np.int32)
+        step = np.zeros(Bsz)
+        iters_total = np.zeros(Bsz, dtype=np.int64)
+        hist_step = np.zeros((Bsz, sc.max_pass))
+        out = L.ScpResult(passes=_ip(passes), scp_status=_ip(scp_status), step=_dp(step),
+                          iters_total=iters_total.ctypes.data_as(C.POINTER(C.c_int64)), hist_step=_dp(hist_step))
+        self._check(self._L.admmb_scp_solve(self._h, C.byref(pb), C.byref(sc), C.byref(op), C.byref(res.c), C.byref(out)))
+        info = res.hist_dict()
+        info.update(passes=passes, scp_status=scp_status, step=step, iters_total=iters_total, hist_step=hist_step,
+                    scp_stats=list(out.stats), linearise_ms=out.linearise_ms)
+        return res.x, res.z, res.u, info
+
+    def k_scp_linearise(self, N: int, scp: dict, xref: np.ndarray, s0: np.ndarray | None = None):
+        """One linearisation pass in math layout: about xref [B, n] (s0 None) or along the nonlinear trajectory from s0
+        under xref's controls (-> that trajectory as well).  -> A (B,N,6,6), B (B,N,6,3), c (B,N,6), xref."""
+        xr = np.array(xref, dtype=np.float64, order="C")
+        Bsz = xr.shape[0]
+        A = np.zeros((Bsz, N, 6, 6))
+        Bm = np.zeros((Bsz, N, 3, 6))
+        c = np.zeros((Bsz, N, 6))
+        s0c = None if s0 is None else np.ascontiguousarray(s0, dtype=np.float64)
+        sc = make_scp(dict(scp, max_pass=scp.get("max_pass", 1)))
+        self._check(self._L.admmb_k_scp_linearise(self._h, int(N), Bsz, C.byref(sc), int(s0 is not None), _dp(s0c),
+                                                  _dp(xr), _dp(A), _dp(Bm), _dp(c)))
+        return (np.ascontiguousarray(np.swapaxes(A, -1, -2)), np.ascontiguousarray(np.swapaxes(Bm, -1, -2)), c, xr)
 
     def upload_generated(self, prob: dict, gen: dict, opts: dict):
         m = to_c_layout(prob)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ADMMB_VERSION 200
+#define ADMMB_VERSION 210
 
 /* return codes */
 enum {
@@ -193,6 +193,43 @@ int admmb_upload_generated(admmb_handle h, const admmb_problem *prob, const admm
                            const admmb_opts *opts);
 int admmb_solve_generated(admmb_handle h, const admmb_problem *prob, const admmb_generator *gen,
                           const admmb_opts *opts, admmb_result *res);
+/* ---- sequential convex programming on the resident batch ------------------------------------------
+ * The caller AFTER the hot path: nonlinear dynamics are re-linearised about each problem's own reference trajectory ON
+ * THE DEVICE (RK4 of the state and its variational equations per stage -> per-problem A_k, B_k, c_k written straight
+ * into the arrays the factor kernel reads), the batched ADMM kernels solve the convex subproblem warm-started from the
+ * previous pass, and a problem leaves the loop when max|x - x_ref| <= tol_abs + tol_rel max|x| (per-problem early exit:
+ * results do not depend on how the batch is sharded).  The first reference is the free drift from s0.  Only s0, the block
+ * table and (optionally) q / per-problem Q, R are uploaded; prob->A, B, c, dyn_batched are ignored.
+ * Oracle: oracle/scp_ocp.py (same IEEE operations in the same order; every pass is bit-identical). */
+enum {
+    ADMMB_SCP_NL_CIRCULAR = 1    /* deputy about a chief on a circular orbit of radius R0: LVLH frame, full two-body
+                                    gravity, zero-order-hold thrust acceleration (linearised at r = 0: Clohessy-Wiltshire) */
+};
+typedef struct admmb_scp {
+    int32_t model;               /* ADMMB_SCP_*                                                  */
+    int32_t substeps;            /* RK4 steps per stage (0 = 8)                                  */
+    double T;                    /* stage length                                                 */
+    double nmm;                  /* mean motion (0 = 1)                                          */
+    double R0;                   /* radius of the chief's orbit, in the problem's length unit    */
+    int32_t max_pass;            /* linearise + solve passes at most (>= 1)                      */
+    double tol_abs, tol_rel;     /* per-problem stop: max|x - x_ref| <= tol_abs + tol_rel max|x| */
+} admmb_scp;
+/* per-problem SCP outputs; caller-allocated, any pointer may be NULL */
+typedef struct admmb_scp_result {
+    int32_t *passes;             /* [batch] passes made                                          */
+    int32_t *scp_status;         /* [batch] 0: trajectory converged, 1: max_pass reached         */
+    double *step;                /* [batch] max|x - x_ref| of the last pass                      */
+    int64_t *iters_total;        /* [batch] ADMM iterations over all passes                      */
+    double *hist_step;           /* [max_pass x batch] step per pass, NaN after the exit         */
+    int64_t stats[4];            /* SCP-converged problems, sum of ADMM iterations over all passes, max passes,
+                                    sum of passes                                                 */
+    double linearise_ms;         /* device time of the linearisation kernels (CUDA events, max over GPUs) */
+} admmb_scp_result;
+/* upload + SCP loop + download.  `res` receives x, z, u, iters, status and the finals of every problem's LAST convex
+ * solve; res->stats[1] counts the ADMM iterations of all passes, res->device_ms the whole loop.  opts: adapt_rho and
+ * history must be off, xupdate auto / riccati.  */
+int admmb_scp_solve(admmb_handle h, const admmb_problem *prob, const admmb_scp *scp, const admmb_opts *opts,
+                    admmb_result *res, admmb_scp_result *scp_res);
 /* launch the device work of GPU 0 on a caller-owned cudaStream_t (NULL: the library's own) */
 int admmb_set_stream(admmb_handle h, void *cuda_stream);
 
@@ -219,6 +256,12 @@ int admmb_k_xupdate_dense(admmb_handle h, int32_t N, int64_t batch, const double
 /* the generated stage matrices themselves, A [6x6xNxBd], B [6x3xNxBd] (Bd = 1 for the CW kinds, batch
  * for ELLIPTIC), for comparison with oracle/gen_ocp.py                                              */
 int admmb_k_generate(admmb_handle h, int32_t N, int64_t batch, const admmb_generator *gen, double *A, double *B);
+
+/* the stage records of one linearisation pass about xref [n x batch] (shoot = 0), or along the nonlinear
+ * trajectory from s0 [6 x batch] under the controls of xref (shoot = 1; xref is then overwritten with that trajectory):
+ * A [6x6xNxbatch], B [6x3xNxbatch], c [6xNxbatch], for comparison with oracle/scp_ocp.py linearise / shoot       */
+int admmb_k_scp_linearise(admmb_handle h, int32_t N, int64_t batch, const admmb_scp *scp, int32_t shoot,
+                          const double *s0, double *xref, double *A, double *B, double *c);
 
 #ifdef __cplusplus
 }
