@@ -15,11 +15,19 @@ namespace admmb {
 
 // slot = [rows][32 lanes] doubles: 46 record rows + 6 (chat / c).  Always 52 rows: with the smaller 46-row slots two
 // CTAs fit an SM, the block scheduler co-locates them while other SMs idle, and the kernel gets 8 % slower (measured).
-__host__ __device__ constexpr int ppt_slot_bytes(bool) { return 52 * 256; }
+//
+// GEN = true (round 2, for the SCP loop of scp.cuh and every other per-problem model WITHOUT the in-plane / cross-track
+// structure): the same ring over the generic 156-double records -- a backward slot is record rows 0..83 (K, Acl, Hinv, E)
+// + chat, a forward slot K + rows 84..149 (A, B, c), 90 rows of 32 lanes -- read by admm_iteration_fast through
+// staged_row() (kernels.cuh).  Without it these models ran 475 us per iteration at 4,096 problems (84-90 dependent-on-
+// latency global loads per thread and stage).
+__host__ __device__ constexpr int ppt_slot_bytes(bool, bool gen = false) { return (gen ? 90 : 52) * 256; }
 constexpr int PPT_SLOTS = 8;                       // ring slots per CTA = warps x slots per warp: (4, 2) or (1, 8)
 
 struct PpTmaMaps {
-    CUtensorMap m46, m10, m30, m6;                 // boxes of 46 / 10 / 30 / 6 rows x 32 columns over fac_dec [FD*N][ld]
+    // boxes of [rows] x 32 columns.  Decoupled records (fac_dec [FD*N][ld]): backward 46, forward 10 + 30, c / chat 6.
+    // Generic records (fac [FS*N][ld]): backward 84, forward 18 + 66, chat 6.
+    CUtensorMap mB, mF0, mF1, m6;
 };
 
 __device__ __forceinline__ void ppt_tma(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar)
@@ -32,7 +40,7 @@ __device__ __forceinline__ void ppt_tma(uint32_t dst, const CUtensorMap *map, in
 // (one stage ahead) are enough when many warps share an SM; a lone warp -- the narrow tail of a solve, where the slowest
 // problems set the time -- needs the whole DRAM latency (~800 ns) covered by requests in flight, i.e. >= 6 stages of
 // ~150 ns, so narrow working sets run one warp per CTA with an eight-slot ring (same shared memory per CTA).
-template <bool HAS_C, int R>
+template <bool HAS_C, int R, bool GEN = false>
 struct PpStaging {
     const PpTmaMaps *maps;
     uint32_t slot0, bar0;                          // this warp's ring
@@ -42,21 +50,33 @@ struct PpStaging {
     bool lane0;
 
     // step s uses slot s % R with mbarrier phase (s / R) & 1
-    __device__ __forceinline__ uint32_t slot(unsigned s) const { return slot0 + (s & (R - 1)) * (uint32_t)ppt_slot_bytes(HAS_C); }
+    __device__ __forceinline__ uint32_t slot(unsigned s) const { return slot0 + (s & (R - 1)) * (uint32_t)ppt_slot_bytes(HAS_C, GEN); }
     __device__ __forceinline__ uint32_t bar(unsigned s) const { return bar0 + 8u * (s & (R - 1)); }
     __device__ __forceinline__ void issue_bwd(int k, unsigned s) const
     {
         const uint32_t d = slot(s), b = bar(s);
+        if (GEN) {
+            mbar_expect_tx(b, (uint32_t)((F_A + (HAS_C ? 6 : 0)) * 256));
+            ppt_tma(d, &maps->mB, col0, k * FS, b);
+            if (HAS_C) ppt_tma(d + F_A * 256, &maps->m6, col0, k * FS + F_CHAT, b);
+            return;
+        }
         mbar_expect_tx(b, (uint32_t)((46 + (HAS_C ? 6 : 0)) * 256));
-        ppt_tma(d, &maps->m46, col0, k * FD, b);
+        ppt_tma(d, &maps->mB, col0, k * FD, b);
         if (HAS_C) ppt_tma(d + 46 * 256, &maps->m6, col0, k * FD + D_CHAT, b);
     }
     __device__ __forceinline__ void issue_fwd(int k, unsigned s) const
     {
         const uint32_t d = slot(s), b = bar(s);
+        if (GEN) {
+            mbar_expect_tx(b, (uint32_t)((18 + 66) * 256));
+            ppt_tma(d, &maps->mF0, col0, k * FS + F_K, b);
+            ppt_tma(d + 18 * 256, &maps->mF1, col0, k * FS + F_A, b);
+            return;
+        }
         mbar_expect_tx(b, (uint32_t)((40 + (HAS_C ? 6 : 0)) * 256));
-        ppt_tma(d, &maps->m10, col0, k * FD, b);
-        ppt_tma(d + 10 * 256, &maps->m30, col0, k * FD + D_AIN, b);
+        ppt_tma(d, &maps->mF0, col0, k * FD, b);
+        ppt_tma(d + 10 * 256, &maps->mF1, col0, k * FD + D_AIN, b);
         if (HAS_C) ppt_tma(d + 40 * 256, &maps->m6, col0, k * FD + D_C, b);
     }
     // q-th stage of an iteration: backward stages N-1 .. 0, then forward stages 0 .. N-1
@@ -98,7 +118,7 @@ struct PpStaging {
 // dynamic smem: [16 B mbarrier][par shared ? 8*nb doubles : 0][nb ints, padded][PPT_SLOTS ring mbarriers]
 //               [pad to 128][PPT_SLOTS slots of ppt_slot_bytes(HAS_C)]
 // W warps per CTA, each with a ring of R = PPT_SLOTS / W slots
-template <bool HAS_C, bool HAS_Q, bool ADAPT, int W>
+template <bool HAS_C, bool HAS_Q, bool ADAPT, int W, bool GEN = false>
 __global__ void __launch_bounds__(W * 32, 1)
 k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant__ PpTmaMaps maps)
 {
@@ -141,13 +161,13 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
     if (!__any_sync(0xffffffffu, was_running)) return;
 
     FacRef<false> F;
-    F.base = P.fac_dec + p;
+    F.base = (GEN ? P.fac : P.fac_dec) + p;
     F.ld = P.ld;
     F.sbase = 0;
     unsigned step = 0;
-    PpStaging<HAS_C, R> stg;
+    PpStaging<HAS_C, R, GEN> stg;
     stg.maps = &maps;
-    stg.slot0 = ring + (uint32_t)(warp * R) * ppt_slot_bytes(HAS_C);
+    stg.slot0 = ring + (uint32_t)(warp * R) * ppt_slot_bytes(HAS_C, GEN);
     stg.bar0 = ring_bars + 8u * (warp * R);
     stg.lane8 = 8u * lane;
     stg.col0 = col0;
@@ -179,7 +199,10 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
         const bool run = st == ST_RUNNING;
         if (!__any_sync(0xffffffffu, run)) break;
         double nr[5];
-        admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C, R>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
+        if (GEN)
+            admm_iteration_fast<false, true, HAS_C, HAS_Q, ADAPT, GlobalIO, PpStaging<HAS_C, R, GEN>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, GlobalIO(), run || zomb, stg);
+        else
+            admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C, R, GEN>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
         if (!run) continue;
         ++it;
         sigma = 1.0;
@@ -212,7 +235,7 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
                                              ldr, rho, bdS, P.fac_rw + p, P.ld);
                 atomicAdd(P.refac_count, 1ULL);
                 if (bad) { st = ST_NAN; finished(); continue; }
-                pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
+                if (!GEN) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
                 __threadfence();                                   // the next iteration's TMA reads must see the new record
                 asm volatile("fence.proxy.async.global;" ::: "memory");
             }

@@ -529,6 +529,20 @@ __device__ __forceinline__ void admm_iteration(const IterParams &P, const size_t
 //   * factor rows are read with 128-bit loads (LDS.128 when the factor is staged in shared memory).
 // Operation order per accumulator is exactly that of admm_iteration / the oracle.
 // ------------------------------------------------------------------------------------------------
+// hooks of the per-stage factor staging; the default does nothing (factor already addressable)
+struct NoStaging {
+    template <class FR> __device__ __forceinline__ void iter_begin(FR &) {}
+    template <class FR> __device__ __forceinline__ void bwd_begin(int, FR &) {}
+    template <class FR> __device__ __forceinline__ void fwd_begin(int, FR &) {}
+    __device__ __forceinline__ void stage_end() {}
+};
+
+// Per-problem factors (FSH = false) with FSMEM = true: the current stage's record rows of the warp's 32 problems have
+// been staged in shared memory by TMA (iterate_pptma.cuh, generic records): [row][32 lanes] doubles, F.sbase = slot + 8 *
+// lane.  A backward slot holds record rows 0..83 (K, Acl, Hinv, E) followed by chat, a forward slot K followed by rows
+// 84..149 (A, B, c): in both, record offset `off` sits in slot row off (off < 84) or off - 66.
+__device__ __forceinline__ uint32_t staged_row(int off) { return (uint32_t)(off < F_A ? off : off - 66) * 256u; }
+
 template <bool FSH, bool FSMEM>
 __device__ __forceinline__ void fac_row6(const FacRef<FSH> &F, int k, int off, double (&r)[6])
 {
@@ -540,6 +554,9 @@ __device__ __forceinline__ void fac_row6(const FacRef<FSH> &F, int k, int off, d
         const double2 *q = reinterpret_cast<const double2 *>(F.base + k * FS + off);
         const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
         r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
+    } else if (FSMEM) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r[i] = lds64(F.sbase + staged_row(off + i));
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i) r[i] = F.base[((size_t)k * FS + off + i) * F.ld];
@@ -556,6 +573,9 @@ __device__ __forceinline__ void fac_row3(const FacRef<FSH> &F, int k, int off, d
         const double2 *q = reinterpret_cast<const double2 *>(F.base + k * FS + off);
         const double2 a = __ldg(q), b = __ldg(q + 1);
         r[0] = a.x; r[1] = a.y; r[2] = b.x;
+    } else if (FSMEM) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = lds64(F.sbase + staged_row(off + i));
     } else {
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = F.base[((size_t)k * FS + off + i) * F.ld];
@@ -594,13 +614,14 @@ __device__ __forceinline__ void block_update(int type, ParFn par, double rinv, d
     }
 }
 
-template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, class IO = GlobalIO>
-__device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const size_t p, const FacRef<FSH> F,
+template <bool FSH, bool FSMEM, bool HAS_C, bool HAS_Q, bool ADAPT, class IO = GlobalIO, class Staging = NoStaging>
+__device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const size_t p, FacRef<FSH> F,
                                                     const int *bdesc, const uint32_t par_sbase, const double rho,
                                                     const double sigma, double (&nr)[5], const IO io = IO(),
-                                                    const bool act = true)
+                                                    const bool act = true, Staging stg = Staging())
 {
     const int N = P.N;
+    stg.iter_begin(F);
     const size_t ld = P.ld;
     const double rinv = 1.0 / rho;
     // in this pattern the split blocks are ctrl_0 .. ctrl_{N-1} followed by the terminal blocks, so the
@@ -663,6 +684,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     const double *zl = zp + (ptrdiff_t)(N - 3) * ld3, *ul = up + (ptrdiff_t)(N - 3) * ld3;   // rows of stage k-2
     double *ds = dp + (ptrdiff_t)(N - 1) * ld3;                                               // rows of stage k
     auto bwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], const double (&g)[6], double (&pn)[6]) {
+        stg.bwd_begin(k, F);
         double ra[3];
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
@@ -716,6 +738,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
 #pragma unroll
             for (int i = 0; i < 6; ++i) pn[i] = fma(ar[i], gg[l], pn[i]);
         }
+        stg.stage_end();
     };
     {
         int k = N - 1;
@@ -746,6 +769,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
     double *zw = zp, *uw = up;                                                  // rows of stage k (stores)
     auto fwd_stage = [&](const int k, double (&zc)[3], double (&uc)[3], double (&dc)[3], const double (&s)[6],
                          double (&sn)[6]) {
+        stg.fwd_begin(k, F);
         double a[3], zo[3], uo[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -782,9 +806,10 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             for (int l = 1; l < 6; ++l) acc = fma(ar[l], s[l], acc);
 #pragma unroll
             for (int j = 0; j < 3; ++j) acc = fma(br[j], a[j], acc);
-            if (HAS_C) acc = acc + F(k, F_C + i);
+            if (HAS_C) acc = acc + ((!FSH && FSMEM) ? lds64(F.sbase + staged_row(F_C + i)) : F(k, F_C + i));
             sn[i] = acc;
         }
+        stg.stage_end();
     };
     bool s_in_A = true;
     {
@@ -941,14 +966,6 @@ __device__ __forceinline__ double dec_ld1(const FacRef<FSH> &F, int k, int off)
     if (FSMEM) return lds64(F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u);
     return F.base[((size_t)k * FD + off) * F.ld];
 }
-
-// hooks of the per-stage factor staging; the default does nothing (factor already addressable)
-struct NoStaging {
-    template <class FR> __device__ __forceinline__ void iter_begin(FR &) {}
-    template <class FR> __device__ __forceinline__ void bwd_begin(int, FR &) {}
-    template <class FR> __device__ __forceinline__ void fwd_begin(int, FR &) {}
-    __device__ __forceinline__ void stage_end() {}
-};
 
 // PD = prefetch distance in stages (even): 2 under the 128-register cap, 4 in the uncapped build, where a
 // lone warp per sub-partition has nothing else to hide the global-load latency behind.

@@ -1,8 +1,9 @@
-// admm_mex.cpp -- the thin MEX gateway  [x, z, u, hist] = admm_mex(prob, opts)
+// admm_mex.cpp -- the thin MEX gateway  [x, z, u, hist] = admm_mex(prob, opts [, scp])
 // (layer L2 of SURVEY.md 1.2; BASELINE.json north_star: "MATLAB host code calls CUDA through a thin
 // C-ABI MEX layer, with no gpuArray").  It validates mxArray fields, extracts raw pointers
 // (zero-copy on the host side: MATLAB's column-major arrays ARE the C-ABI layout), allocates the
-// outputs and calls admmb_solve.  No math happens here.
+// outputs and calls admmb_solve -- or, with a third argument, admmb_scp_solve (the stage matrices are
+// then re-linearised on the device each pass, prob carries N instead of A, B).  No math happens here.
 //
 // Build (on a machine that has MATLAB):  mex -R2018a admm_mex.cpp -I../../include -L../lib -ladmm_b200
 // In this repository it is only syntax-checked against mex/stub/mex.h (no MATLAB in the image).
@@ -86,23 +87,26 @@ mxArray *new_double(size_t rows, size_t cols, double **p)
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
-    if (nrhs < 1 || nrhs > 2 || !mxIsStruct(prhs[0]) || (nrhs == 2 && !mxIsStruct(prhs[1])))
-        mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "usage: [x,z,u,hist] = admm_mex(prob, opts)");
+    if (nrhs < 1 || nrhs > 3 || !mxIsStruct(prhs[0]) || (nrhs >= 2 && !mxIsStruct(prhs[1])) || (nrhs == 3 && !mxIsStruct(prhs[2])))
+        mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "usage: [x,z,u,hist] = admm_mex(prob, opts [, scp])");
     if (nlhs > 4) mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "at most four outputs");
-    const mxArray *P = prhs[0], *O = nrhs == 2 ? prhs[1] : nullptr;
+    const mxArray *P = prhs[0], *O = nrhs >= 2 ? prhs[1] : nullptr, *S = nrhs == 3 ? prhs[2] : nullptr;
 
     // ---- problem: raw pointers into MATLAB's own (read-only) buffers
     admmb_problem pb;
     std::memset(&pb, 0, sizeof(pb));
-    const mxArray *A = field(P, "A", true), *B = field(P, "B", true), *s0 = field(P, "s0", true);
+    const mxArray *A = field(P, "A", !S), *B = field(P, "B", !S), *s0 = field(P, "s0", true);
+    if (S) A = B = nullptr;                               // SCP: the model is produced on the device
     const mxArray *bt = field(P, "block_type", true), *bp = field(P, "block_par", true);
     const mxArray *c = field(P, "c", false), *Q = field(P, "Q", false), *R = field(P, "R", false);
     const mxArray *q = field(P, "q", false), *z0 = field(P, "z0", false), *u0 = field(P, "u0", false);
     const mxArray *rho0 = field(P, "rho0", false);
-    if (dim(A, 0) != 6 || dim(A, 1) != 6 || dim(B, 0) != 6 || dim(B, 1) != 3 || dim(s0, 0) != 6)
+    if (dim(s0, 0) != 6 || (!S && (dim(A, 0) != 6 || dim(A, 1) != 6 || dim(B, 0) != 6 || dim(B, 1) != 3)))
         mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "A must be 6x6xNxBd, B 6x3xNxBd, s0 6xBsz");
-    const size_t N = dim(A, 2), Bd = dim(A, 3), Bsz = dim(s0, 1), n = 9 * N + 6, nb = 3 * N + 2;
-    if (dim(B, 2) != N || dim(B, 3) != Bd || (Bd != 1 && Bd != Bsz))
+    const size_t Bsz = dim(s0, 1);
+    const size_t N = S ? (size_t)mxGetScalar(field(P, "N", true)) : dim(A, 2), Bd = S ? Bsz : dim(A, 3);
+    const size_t n = 9 * N + 6, nb = 3 * N + 2;
+    if (!S && (dim(B, 2) != N || dim(B, 3) != Bd || (Bd != 1 && Bd != Bsz)))
         mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "A and B must agree in N and be shared (Bd=1) or per problem (Bd=Bsz)");
     if (!mxIsInt32(bt) || mxGetNumberOfElements(bt) != nb)
         mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "block_type must be int32 with 3N+2 entries");
@@ -121,7 +125,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "prob.q must be n x 1 or n x Bsz");
     pb.N = (int32_t)N;
     pb.batch = (int64_t)Bsz;
-    pb.A = dptr(A, "A"); pb.B = dptr(B, "B"); pb.c = dptr(c, "c"); pb.Q = dptr(Q, "Q"); pb.R = dptr(R, "R");
+    pb.A = dptr(A, "A"); pb.B = dptr(B, "B"); pb.c = S ? nullptr : dptr(c, "c"); pb.Q = dptr(Q, "Q"); pb.R = dptr(R, "R");
     pb.dyn_batched = Bd > 1;
     pb.q = dptr(q, "q");
     pb.q_batched = q && mxGetNumberOfElements(q) == n * Bsz && Bsz > 1;
@@ -155,6 +159,21 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     op.tf32_refresh = (int32_t)opt_scalar(O, "tf32_refresh", 0);
     const int gpus = (int)opt_scalar(O, "gpus", 0);
 
+    // ---- SCP parameters (third argument): model, stage length, orbit radius, passes, trajectory tolerances
+    admmb_scp sc;
+    std::memset(&sc, 0, sizeof(sc));
+    if (S) {
+        static const char *const models[] = {"", "nl_circular"};
+        sc.model = opt_enum(S, "model", models, 2, ADMMB_SCP_NL_CIRCULAR);
+        sc.substeps = (int32_t)opt_scalar(S, "substeps", 0);
+        sc.T = opt_scalar(S, "T", 0.0);
+        sc.nmm = opt_scalar(S, "nmm", 0.0);
+        sc.R0 = opt_scalar(S, "R0", 0.0);
+        sc.max_pass = (int32_t)opt_scalar(S, "max_pass", 10);
+        sc.tol_abs = opt_scalar(S, "tol_abs", 0.0);
+        sc.tol_rel = opt_scalar(S, "tol_rel", 1e-6);
+    }
+
     // ---- handle: created once, kept across calls (CUDA context, device buffers, worker threads)
     if (g_handle && gpus != g_gpus) at_exit();
     if (!g_handle) {
@@ -171,8 +190,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     plhs[0] = new_double(n, Bsz, &res.x);
     mxArray *mz = new_double(n, Bsz, &res.z), *mu = new_double(n, Bsz, &res.u);
     static const char *names[] = {"iters", "status", "r_norm", "s_norm", "eps_pri", "eps_dual", "rho", "hist_r_norm",
-                                  "hist_s_norm", "hist_eps_pri", "hist_eps_dual", "hist_rho", "stats", "device_ms"};
-    mxArray *H = mxCreateStructMatrix(1, 1, 14, names);
+                                  "hist_s_norm", "hist_eps_pri", "hist_eps_dual", "hist_rho", "stats", "device_ms",
+                                  "scp_passes", "scp_status", "scp_step", "scp_iters_total", "scp_hist_step", "scp_stats"};
+    mxArray *H = mxCreateStructMatrix(1, 1, 20, names);
     mxArray *it = mxCreateNumericMatrix(Bsz, 1, mxINT32_CLASS, mxREAL), *st = mxCreateNumericMatrix(Bsz, 1, mxINT32_CLASS, mxREAL);
     res.iters = mxGetInt32s(it);
     res.status = mxGetInt32s(st);
@@ -191,7 +211,29 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         mxSetField(H, 0, "hist_rho", new_double((size_t)op.max_iter, Bsz, &res.hist_rho));
     }
 
-    int rc = admmb_solve(g_handle, &pb, &op, &res);           // blocking; worker threads never touch mx*/mex*
+    int rc;
+    if (S) {
+        admmb_scp_result so;
+        std::memset(&so, 0, sizeof(so));
+        mxArray *ps = mxCreateNumericMatrix(Bsz, 1, mxINT32_CLASS, mxREAL), *ss = mxCreateNumericMatrix(Bsz, 1, mxINT32_CLASS, mxREAL);
+        mxArray *ti = mxCreateNumericMatrix(Bsz, 1, mxINT64_CLASS, mxREAL);
+        so.passes = mxGetInt32s(ps);
+        so.scp_status = mxGetInt32s(ss);
+        so.iters_total = mxGetInt64s(ti);
+        mxSetField(H, 0, "scp_passes", ps);
+        mxSetField(H, 0, "scp_status", ss);
+        mxSetField(H, 0, "scp_iters_total", ti);
+        mxSetField(H, 0, "scp_step", new_double(Bsz, 1, &so.step));
+        mxSetField(H, 0, "scp_hist_step", new_double((size_t)(sc.max_pass > 0 ? sc.max_pass : 1), Bsz, &so.hist_step));
+        rc = admmb_scp_solve(g_handle, &pb, &sc, &op, &res, &so);
+        if (rc == ADMMB_OK) {
+            mxArray *sst = mxCreateNumericMatrix(4, 1, mxINT64_CLASS, mxREAL);
+            std::memcpy(mxGetInt64s(sst), so.stats, sizeof(so.stats));
+            mxSetField(H, 0, "scp_stats", sst);
+        }
+    } else {
+        rc = admmb_solve(g_handle, &pb, &op, &res);           // blocking; worker threads never touch mx*/mex*
+    }
     if (rc != ADMMB_OK) mexErrMsgIdAndTxt(code_name(rc), "%s", admmb_last_error(g_handle));
 
     mxArray *stats = mxCreateNumericMatrix(4, 1, mxINT64_CLASS, mxREAL);
