@@ -615,7 +615,7 @@ void Shard::scp_solve(const admmb_scp *sc, const admmb_opts *op, admmb_result *r
         k_output<false, true><<<gb, 128, 0, stream>>>(N, batch, ld, fac.p, s0.p, d.p, z.p, u.p, usc.p, bdesc.p, iters.p, xo.p,
                                                       nullptr, nullptr);
         CK(cudaMemsetAsync(scp_count.p, 0, sizeof(int), stream));
-        k_scp_step<<<gb, 128, 0, stream>>>(batch, n, ld, pass, sc->tol_abs, sc->tol_rel, xo.p, scp_xref.p, iters.p,
+        k_scp_step<<<gb, 128, 0, stream>>>(batch, n, ld, pass, sc->tol_abs, sc->tol_rel, xo.p, scp_xref.p, iters.p, status.p,
                                            scp_active.p, scp_passes.p, scp_status.p, scp_step.p, scp_iters.p, scp_hist.p,
                                            scp_count.p);
         launches += 2;

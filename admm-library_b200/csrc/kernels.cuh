@@ -368,6 +368,16 @@ __device__ __forceinline__ double lds64(uint32_t a)
     asm("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
     return r;
 }
+// A read of a ring slot that TMA refills (iterate_pptma.cuh): `volatile` + the memory clobber keep it between the mbarrier
+// wait that publishes the slot and the __syncwarp that releases it.  A plain asm load has no side effects and depends
+// only on its address, which is known before the wait -- the compiler may hoist it above the wait and read the slot's
+// previous contents (seen with the two-slot ring of the generic-record kernel: NaN at > 4,736 problems).
+__device__ __forceinline__ double lds64_ordered(uint32_t a)
+{
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a) : "memory");
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // One ADMM iteration of problem p (rows a2 + a3 + a4 fused): backward sweep, then a forward sweep
@@ -556,7 +566,7 @@ __device__ __forceinline__ void fac_row6(const FacRef<FSH> &F, int k, int off, d
         r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
     } else if (FSMEM) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) r[i] = lds64(F.sbase + staged_row(off + i));
+        for (int i = 0; i < 6; ++i) r[i] = lds64_ordered(F.sbase + staged_row(off + i));
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i) r[i] = F.base[((size_t)k * FS + off + i) * F.ld];
@@ -575,7 +585,7 @@ __device__ __forceinline__ void fac_row3(const FacRef<FSH> &F, int k, int off, d
         r[0] = a.x; r[1] = a.y; r[2] = b.x;
     } else if (FSMEM) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = lds64(F.sbase + staged_row(off + i));
+        for (int i = 0; i < 3; ++i) r[i] = lds64_ordered(F.sbase + staged_row(off + i));
     } else {
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = F.base[((size_t)k * FS + off + i) * F.ld];
@@ -806,7 +816,7 @@ __device__ __forceinline__ void admm_iteration_fast(const IterParams &P, const s
             for (int l = 1; l < 6; ++l) acc = fma(ar[l], s[l], acc);
 #pragma unroll
             for (int j = 0; j < 3; ++j) acc = fma(br[j], a[j], acc);
-            if (HAS_C) acc = acc + ((!FSH && FSMEM) ? lds64(F.sbase + staged_row(F_C + i)) : F(k, F_C + i));
+            if (HAS_C) acc = acc + ((!FSH && FSMEM) ? lds64_ordered(F.sbase + staged_row(F_C + i)) : F(k, F_C + i));
             sn[i] = acc;
         }
         stg.stage_end();
@@ -951,7 +961,7 @@ __device__ __forceinline__ void dec_ld(const FacRef<FSH> &F, int k, int off, dou
         // K (0..9), A, B (10..39) [+ c] for the forward sweep; row = off below 46, off - 36 above; 256 B per row
         const uint32_t a = F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u;
 #pragma unroll
-        for (int i = 0; i < W; ++i) r[i] = lds64(a + 256u * i);
+        for (int i = 0; i < W; ++i) r[i] = lds64_ordered(a + 256u * i);
     } else {
 #pragma unroll
         for (int i = 0; i < W; ++i) r[i] = ADMMB_LD(F.base + ((size_t)k * FD + off + i) * F.ld);
@@ -963,7 +973,7 @@ template <bool FSH, bool FSMEM>
 __device__ __forceinline__ double dec_ld1(const FacRef<FSH> &F, int k, int off)
 {
     if (FSH) return F.base[k * FD + off];
-    if (FSMEM) return lds64(F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u);
+    if (FSMEM) return lds64_ordered(F.sbase + (uint32_t)(off < 46 ? off : off - 36) * 256u);
     return F.base[((size_t)k * FD + off) * F.ld];
 }
 

@@ -168,10 +168,12 @@ __global__ void k_scp_init(int64_t batch, size_t ld, int *active, int *passes, i
 }
 
 // end of a pass: how far did the trajectory move?  step = max |x - xref|, scale = max |x| (NaN if any entry is), the
-// reference becomes x, and the problem leaves the loop when step <= tol_abs + tol_rel scale (oracle/scp_ocp.py scp_solve)
+// reference becomes x, and the problem leaves the loop when step <= tol_abs + tol_rel scale and its convex solve converged
+// (oracle/scp_ocp.py scp_solve)
 __global__ void __launch_bounds__(128) k_scp_step(int64_t batch, int n, size_t ld, int pass, double tol_abs, double tol_rel,
                                                   const double *__restrict__ x, double *__restrict__ xref,
-                                                  const int *__restrict__ iters, int *active, int *passes, int *scp_status,
+                                                  const int *__restrict__ iters, const int *__restrict__ status, int *active,
+                                                  int *passes, int *scp_status,
                                                   double *step_out, long long *iters_total, double *hist_step,
                                                   int *n_active)
 {
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(128) k_scp_step(int64_t batch, int n, size_t l
     step_out[p] = step;
     if (hist_step) hist_step[(size_t)(pass - 1) * ld + p] = step;
     iters_total[p] += (long long)iters[p];
-    if (step <= tol_abs + tol_rel * scale) {
+    if (step <= tol_abs + tol_rel * scale && status[p] == ST_CONVERGED) {   // the last convex solve must itself have converged
         active[p] = 0;
         scp_status[p] = 0;
     } else {

@@ -197,8 +197,9 @@ int admmb_solve_generated(admmb_handle h, const admmb_problem *prob, const admmb
  * The caller AFTER the hot path: nonlinear dynamics are re-linearised about each problem's own reference trajectory ON
  * THE DEVICE (RK4 of the state and its variational equations per stage -> per-problem A_k, B_k, c_k written straight
  * into the arrays the factor kernel reads), the batched ADMM kernels solve the convex subproblem warm-started from the
- * previous pass, and a problem leaves the loop when max|x - x_ref| <= tol_abs + tol_rel max|x| (per-problem early exit:
- * results do not depend on how the batch is sharded).  The first reference is the free drift from s0.  Only s0, the block
+ * previous pass, and a problem leaves the loop when max|x - x_ref| <= tol_abs + tol_rel max|x| and its convex solve
+ * converged (per-problem early exit: results do not depend on how the batch is sharded; opts->max_iter may therefore cap
+ * the early passes -- inexact SCP).  The first reference is the free drift from s0.  Only s0, the block
  * table and (optionally) q / per-problem Q, R are uploaded; prob->A, B, c, dyn_batched are ignored.
  * Oracle: oracle/scp_ocp.py (same IEEE operations in the same order; every pass is bit-identical). */
 enum {
@@ -212,7 +213,7 @@ typedef struct admmb_scp {
     double nmm;                  /* mean motion (0 = 1)                                          */
     double R0;                   /* radius of the chief's orbit, in the problem's length unit    */
     int32_t max_pass;            /* linearise + solve passes at most (>= 1)                      */
-    double tol_abs, tol_rel;     /* per-problem stop: max|x - x_ref| <= tol_abs + tol_rel max|x| */
+    double tol_abs, tol_rel;     /* per-problem stop: max|x - x_ref| <= tol_abs + tol_rel max|x|, last solve converged */
 } admmb_scp;
 /* per-problem SCP outputs; caller-allocated, any pointer may be NULL */
 typedef struct admmb_scp_result {

@@ -343,6 +343,24 @@ def test_full_width_65536_to_tolerance(solver, cpu_oracle, P, kernel_variant):
     assert (h["status"] == 0).mean() > 0.999
 
 
+# ---- per-problem models on working sets wider than 32 x SMs: the TMA-staged kernels then run four warps per CTA with a
+# two-slot ring each (one stage of prefetch), where a slot read that the compiler hoists above the mbarrier wait sees the
+# previous stage's record -- found in round 2 with the generic-record variant (NaN above 4,736 problems); both record
+# layouts are held against the oracle at that width here.
+@pytest.mark.parametrize("coupled", [False, True])
+def test_per_problem_models_wide_working_set(solver, cpu_oracle, P, coupled, kernel_variant):
+    if kernel_variant != "auto":
+        pytest.skip("width-dependent kernel choice: the automatic one is what is under test")
+    if coupled:      # generic 156-double records (no in-plane / cross-track structure), affine term, linear cost
+        prob, opts = P.lqr_tracking(batch=4800, N=12, seed=3, per_problem=True)
+        opts = dict(opts, max_iter=300)
+    else:            # decoupled packed records
+        prob, opts = P.cfg4_elliptic(batch=4800, N=12, seed=14)
+        opts = dict(opts, max_iter=300)
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    assert_bit_identical(got, ref, f"4,800 per-problem models, coupled={coupled}")
+
+
 # ---- receding-horizon step on the resident batch: admmb_shift_resolve against the oracle's warm-started solve
 @pytest.mark.parametrize("k,from_solution", [(1, True), (1, False), (3, False)])
 def test_shift_resolve_matches_oracle_warm_start(pkg, cpu_oracle, P, k, from_solution, kernel_variant):
