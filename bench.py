@@ -543,7 +543,7 @@ def main():
         if time.perf_counter() - t_cfg0 > 110.0:
             configs["scp"] = {"skipped": "time budget of the extra runs used up"}
         else:
-            b_s, N_s = 1024, 50
+            b_s, N_s = 4096, 50
             ps, ss, os_ = pkg.problems.scp_nonlinear_rendezvous(b_s, N_s)
             solver.scp_solve(dict(ps, s0=ps["s0"][:64]), dict(ss, max_pass=2), os_)      # warm-up
             torch.cuda.synchronize()
