@@ -118,6 +118,7 @@ struct Shard {
     DevBuf<int> orig[2], keep_list, fin_list, split_counts, snap;
     int cur_set = -1;
     int64_t width = 0;
+    int64_t n_real = 0;              // columns 0 .. n_real-1 of the working set are problems, the rest whole-warp padding (copies)
     size_t ld_cur = 0;
     template <typename T>
     T *colptr(int c) const
@@ -429,7 +430,8 @@ void Shard::repack(int n_keep, int n_fin)
         CK(cudaGetLastError());
     }
     CK(cudaMemsetAsync(snap.p, 0, sizeof(int) * ld, stream));   // the next working set starts without snapshots
-    if (n_keep == 0) { width = 0; return; }
+    if (n_keep == 0) { width = 0; n_real = 0; return; }
+    n_real = n_keep;
     // Pad the working set to whole warps with COPIES of its last running problem (own columns, same home column):
     // a launch in which one warp has idle lanes runs ~25 % slower on a narrow working set (measured: 8,160 problems
     // 1.62 ms per 50 iterations, 8,161 or 8,191 problems 2.02-2.04 ms).  The copies evolve identically to their
@@ -783,6 +785,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         set_col(C_RAWR, (refac && dyn_batched && has_R) ? rawR.p : nullptr, 8, 9 * N, false);
         cur_set = -1;
         width = batch;
+        n_real = batch;
         ld_cur = ld;
         const bool no_repack = getenv("ADMMB_NO_REPACK") != nullptr;
         const bool zombies_enabled = getenv("ADMMB_NO_ZOMBIES") == nullptr;
@@ -805,6 +808,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             P.chunk = chunk;
             P.ld = ld_cur;
             P.n_active = (int)width;
+            P.n_real = (int)n_real;
             P.orig = cur_set < 0 ? nullptr : orig[cur_set].p;
             const bool zomb = cur_set >= 0 && zombies_enabled;
             P.z_home = zomb ? z.p : nullptr; P.u_home = zomb ? u.p : nullptr; P.d_home = zomb ? d.p : nullptr;
@@ -832,7 +836,9 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             done_iters += chunk;
             // who is still running?
             CK(cudaMemsetAsync(split_counts.p, 0, 2 * sizeof(int), stream));
-            k_split<<<(unsigned)((width + 255) / 256), 256, 0, stream>>>(P.status, (int)width, keep_list.p, fin_list.p,
+            // only the real columns are listed: the padding copies of the last problem (repack) end with this working set --
+            // their source column carries the same state -- so they never pile up and never count in the statistics
+            k_split<<<(unsigned)((n_real + 255) / 256), 256, 0, stream>>>(P.status, (int)n_real, keep_list.p, fin_list.p,
                                                                         split_counts.p);
             ++launches;
             CK(cudaGetLastError());
@@ -858,7 +864,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
                 else chunk = (int)std::min<long long>(chunk_max, std::max<long long>(50, (long long)width * prev / (100LL * cnt[1])));
             }
             if (adapt && P.every > 0 && chunk > P.every) chunk = (chunk / P.every) * P.every;
-            if (cnt[0] == (int)width) continue;                 // nobody finished in this launch
+            if (cnt[0] == (int)n_real) continue;                // nobody finished in this launch
             if (wg_skip) continue;                              // warp-group kernel: no pass to gain from a repack
             if (no_repack && cnt[0] > 0 && cur_set < 0) continue;   // debug: finished lanes just idle
             repack(cnt[0], cnt[1]);
@@ -868,9 +874,9 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
         if (tf32_tail && width > 0 && width <= tail_width && done_iters < op->max_iter) dense_tail(*this, op, done_iters);
         if (width > 0 && cur_set >= 0) {   // max_iter reached between checks: everything left is final
             CK(cudaMemsetAsync(split_counts.p, 0, 2 * sizeof(int), stream));
-            k_iota<<<(unsigned)((width + 127) / 128), 128, 0, stream>>>(fin_list.p, (int)width);
+            k_iota<<<(unsigned)((n_real + 127) / 128), 128, 0, stream>>>(fin_list.p, (int)n_real);
             ++launches;
-            repack(0, (int)width);
+            repack(0, (int)n_real);
         }
     }
     k_stats<<<gb, 128, 0, stream>>>(batch, iters.p, status.p, counters.p);

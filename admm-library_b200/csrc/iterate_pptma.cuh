@@ -233,7 +233,7 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
                 int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
                                              P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
                                              ldr, rho, bdS, P.fac_rw + p, P.ld);
-                atomicAdd(P.refac_count, 1ULL);
+                if (owned && t < P.n_real) atomicAdd(P.refac_count, 1ULL);
                 if (bad) { st = ST_NAN; finished(); continue; }
                 if (!GEN) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
                 __threadfence();                                   // the next iteration's TMA reads must see the new record

@@ -295,6 +295,8 @@ __device__ __forceinline__ void prox_block_dev(int type, ParFn par, double rinv,
 struct IterParams {
     int N, nb, n;
     int n_active;                 // width of the working set (columns 0 .. n_active-1)
+    int n_real;                   // columns n_real .. n_active-1 are whole-warp padding: copies of a running problem that
+                                  // evolve identically and must not count in the statistics
     const int *orig;              // home column of each working-set column (nullptr: identity)
     size_t hist_ld;               // leading dimension of the history arrays (home layout)
     size_t ld;
@@ -1403,7 +1405,7 @@ __global__ void __launch_bounds__(256, LOWOCC ? 1 : 2) k_admm_iterate(const __gr
                         int bad = riccati_factor_dev(P.N, P.rawA + off, P.rawB + off, P.rawc ? P.rawc + off : nullptr,
                                                      P.rawQ ? P.rawQ + off : nullptr, P.rawR ? P.rawR + off : nullptr,
                                                      ldr, rho, bdS, P.fac_rw + p, P.ld);
-                        atomicAdd(P.refac_count, 1ULL);
+                        if ((int)p < P.n_real) atomicAdd(P.refac_count, 1ULL);
                         if (bad) st = ST_NAN;
                         else if (MODE == 2) pack_decoupled_dev(P.N, P.fac_rw + p, P.ld, P.fac_dec_rw + p, P.ld);
                     }

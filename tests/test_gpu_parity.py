@@ -115,6 +115,18 @@ def test_lqr_quadratic_cost_affine_dynamics(solver, cpu_oracle, P, per_problem, 
     assert_bit_identical(got, ref, f"lqr per_problem={per_problem} adapt={adapt}")
 
 
+def test_refactor_count_ignores_whole_warp_padding(solver, cpu_oracle, P):
+    """after a repack the working set is padded to whole warps with copies of a running problem; with a
+    per-problem factor and adaptive rho the copies used to count their refactorisations too.  Short launches, early
+    exits and a ragged batch make padding happen while rho is still adapting."""
+    prob, opts = P.lqr_tracking(batch=75, N=10, seed=21, per_problem=True)
+    opts = dict(opts, max_iter=400, adapt_rho=1, adapt_every=3, adapt_mu=1.5, chunk=6, abstol=1e-4, reltol=1e-4)
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    assert ref[3]["refactor_count"] > 0 and ref[3]["iters"].min() < ref[3]["iters"].max()
+    assert got[3]["refactor_count"] == ref[3]["refactor_count"]
+    assert_bit_identical(got, ref, "refactor count under padding")
+
+
 def test_warm_start_and_rho0(solver, cpu_oracle, P):
     prob, opts = P.cfg2_cw_batch(batch=40, N=20, seed=9)
     opts = dict(opts, max_iter=150)
