@@ -182,6 +182,61 @@ def test_converged_point_satisfies_optimality_conditions_soc(P, cpu_oracle):
             assert np.linalg.norm(zb[3 * k + 2]) <= prob["block_par"][0, 3 * k + 2, 1] + 1e-9
 
 
+@pytest.mark.parametrize("elliptic", [False, True])
+def test_soc_objective_matches_an_independent_nlp_solver(P, cpu_oracle, elliptic):
+    """the thrust-magnitude (second-order-cone) configurations had no independent solver behind
+    them.  The image has no SOCP solver, but the condensed problem is small and convex:
+        min sum_k lam |a_k|_2   s.t.  sum_k G_k a_k = -Phi s0 (terminal point),  |a_k|_2 <= a_max,
+    solved here by scipy's SLSQP with the norm smoothed to sqrt(|a|^2 + eps^2) (eps = 1e-7: the epigraph form t^2 >= |a|^2
+    loses its constraint qualification where a control is exactly zero, and fuel-optimal controls are), for the shared
+    CW model (config 3) and a per-problem elliptic model (config 4).  The ADMM optimum must (i) be feasible, (ii) not
+    exceed the value of SLSQP's feasible point, (iii) agree with it to SLSQP's accuracy."""
+    from scipy.optimize import minimize
+    N, B, eps = 10, 3, 1e-7
+    prob, opts = (P.cfg4_elliptic(batch=B, N=N, seed=8) if elliptic else P.cfg3_lowthrust_soc(batch=B, N=N, seed=5))
+    x, z, u, h = cpu_oracle.solve(prob, dict(opts, max_iter=300000, abstol=1e-9, reltol=1e-9))
+    assert (h["status"] == 0).all()
+    lam, rad = prob["block_par"][0, 2, 0], prob["block_par"][0, 2, 1]
+    for i in range(B):
+        A, Bm = (prob["A"][i], prob["B"][i]) if elliptic else (prob["A"][0], prob["B"][0])
+        G, M = [], np.eye(6)
+        for k in range(N - 1, -1, -1):
+            G.insert(0, M @ Bm[k])
+            M = M @ A[k]
+        Gm, rhs = np.hstack(G), -(M @ prob["s0"][i])
+
+        def f(v):
+            return lam * np.sqrt((v.reshape(N, 3) ** 2).sum(1) + eps * eps).sum()
+
+        def grad(v):
+            a = v.reshape(N, 3)
+            return (lam * a / np.sqrt((a * a).sum(1) + eps * eps)[:, None]).ravel()
+
+        def ball(v):
+            return rad * rad - (v.reshape(N, 3) ** 2).sum(1)
+
+        def ball_jac(v):
+            a = v.reshape(N, 3)
+            J = np.zeros((N, 3 * N))
+            for k in range(N):
+                J[k, 3 * k:3 * k + 3] = -2.0 * a[k]
+            return J
+
+        a0 = np.linalg.lstsq(Gm, rhs, rcond=None)[0]
+        r = minimize(f, a0, jac=grad, method="SLSQP",
+                     constraints=[dict(type="eq", fun=lambda v: Gm @ v - rhs, jac=lambda v: Gm),
+                                  dict(type="ineq", fun=ball, jac=ball_jac)], options=dict(maxiter=5000, ftol=1e-14))
+        # SLSQP may stop with 'positive directional derivative' at this tolerance: what matters is that its point is feasible
+        assert np.abs(Gm @ r.x - rhs).max() <= 1e-7 and ball(r.x).min() >= -1e-8
+        fun = lam * np.linalg.norm(r.x.reshape(N, 3), axis=1).sum()
+        ctrl = z[i, :9 * N].reshape(N, 9)[:, 6:9]
+        nrm = np.linalg.norm(ctrl, axis=1)
+        obj = lam * nrm.sum()
+        assert np.abs(Gm @ ctrl.ravel() - rhs).max() <= 1e-6 and nrm.max() <= rad + 1e-9      # (i)
+        assert obj <= fun * (1.0 + 1e-6)                                                        # (ii)
+        assert abs(obj - fun) <= 1e-5 * fun, (obj, fun)                                         # (iii)
+
+
 # ----------------------------------------------------------------------------- NumPy vs C restatement
 def _close(a, b, tol=1e-10):
     return np.allclose(a, b, rtol=tol, atol=tol, equal_nan=True)
