@@ -562,8 +562,14 @@ def main():
             if not args.no_parity:
                 sys.path.insert(0, ROOT)
                 from oracle import scp_ocp
-                kq = 12
+                kq = 64
+                t0 = time.perf_counter()
                 xo_, zo_, uo_, ho_ = scp_ocp.scp_solve(dict(ps, s0=ps["s0"][:kq]), ss, os_)
+                t_cpu = time.perf_counter() - t0
+                rec["cpu_port"] = {"value": float(ho_["iters_total"].sum()) / t_cpu, "unit": UNIT, "problems": kq,
+                                   "seconds": t_cpu, "kind": "port",
+                                   "what": "oracle/scp_ocp.py (NumPy linearisation + oracle/admm_ocp_cpu.c with OpenMP over the "
+                                           "problems of each pass) on the first problems of the same batch"}
                 rec["parity_checked"] = kq
                 rec["parity_ok"] = bool(np.array_equal(xs[:kq], xo_) and np.array_equal(zs[:kq], zo_) and
                                         np.array_equal(us[:kq], uo_) and np.array_equal(hs["passes"][:kq], ho_["passes"]) and
