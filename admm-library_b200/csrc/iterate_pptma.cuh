@@ -22,6 +22,9 @@ namespace admmb {
 // staged_row() (kernels.cuh).  Without it these models ran 475 us per iteration at 4,096 problems (84-90 dependent-on-
 // latency global loads per thread and stage).
 __host__ __device__ constexpr int ppt_slot_bytes(bool, bool gen = false) { return (gen ? 90 : 52) * 256; }
+#ifndef PPT_DEEP_PD
+#define PPT_DEEP_PD 2                              // prefetch distance (stages) of the iterates in the one-warp-per-CTA form
+#endif
 constexpr int PPT_SLOTS = 8;                       // ring slots per CTA = warps x slots per warp: (4, 2) or (1, 8)
 
 struct PpTmaMaps {
@@ -202,7 +205,7 @@ k_admm_iterate_pptma(const __grid_constant__ IterParams P, const __grid_constant
         if (GEN)
             admm_iteration_fast<false, true, HAS_C, HAS_Q, ADAPT, GlobalIO, PpStaging<HAS_C, R, GEN>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, GlobalIO(), run || zomb, stg);
         else
-            admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, 2, PpStaging<HAS_C, R, GEN>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
+            admm_iteration_dec<false, true, HAS_C, HAS_Q, ADAPT, (W == 1 ? PPT_DEEP_PD : 2), PpStaging<HAS_C, R, GEN>>(P, p, F, bdS, par_sbase, rho, zomb ? 1.0 : sigma, nr, stg, run || zomb);
         if (!run) continue;
         ++it;
         sigma = 1.0;
