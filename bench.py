@@ -558,7 +558,7 @@ def main():
                    "problems": b_s, "trajectory_converged": int(hs["scp_stats"][0]), "passes_max": int(hs["scp_stats"][2]),
                    "passes_mean": hs["scp_stats"][3] / b_s, "admm_iterations_total": int(hs["scp_stats"][1]),
                    "h2d_bytes": int(ps["s0"].nbytes + ps["block_par"].nbytes + ps["block_type"].nbytes),
-                   "kernel": "k_scp_shoot / k_scp_linearise + k_riccati_factor + k_admm_iterate (per-problem model) per pass"}
+                   "kernel": "k_scp_shoot / k_scp_linearise + k_riccati_factor + k_admm_iterate_pptma<GEN> (generic per-problem records through the TMA ring) per pass"}
             if not args.no_parity:
                 sys.path.insert(0, ROOT)
                 from oracle import scp_ocp
