@@ -194,6 +194,10 @@ def scp_solve(prob: dict, scp: dict, opts: dict, solve=None):
                    block_par=sub_of(prob["block_par"], idx))
         if p > 1:
             sub["z0"], sub["u0"] = z[idx], u[idx]
+        else:                                         # an initial warm start given with the problem serves the first pass
+            for key in ("z0", "u0"):
+                if prob.get(key) is not None:
+                    sub[key] = np.asarray(prob[key], dtype=np.float64)[idx]
         xs, zs, us, h = solve(sub, opts)
         x[idx], z[idx], u[idx] = xs, zs, us
         iters[idx], status[idx] = h["iters"], h["status"]

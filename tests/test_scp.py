@@ -203,6 +203,32 @@ def test_scp_solve_matches_oracle(solver, P, B, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(2, 1), (3, 2), (31, 3), (33, 5)])
+def test_scp_tiny_horizons_and_ragged_batches(solver, P, B, N):
+    """Horizons shorter than the TMA ring's prefetch distance, batches that do not fill a warp."""
+    prob, scp, opts = P.scp_nonlinear_rendezvous(B, N, seed=300 + B, scale=10.0, substeps=2, max_pass=6)
+    _assert_scp_equal(solver.scp_solve(prob, scp, opts), scp_ocp.scp_solve(prob, scp, opts))
+
+
+@pytest.mark.gpu
+def test_scp_per_problem_block_parameters_and_initial_warm_start(solver, P):
+    """Per-problem thrust bounds / terminal points (par_batched) travel through the passes; a warm start given with the
+    problem serves the first pass."""
+    B, N = 20, 8
+    prob, scp, opts = P.scp_nonlinear_rendezvous(B, N, seed=51, scale=25.0, substeps=3, max_pass=8)
+    rng = np.random.Generator(np.random.PCG64(6))
+    bp = np.broadcast_to(prob["block_par"], (B,) + prob["block_par"].shape[1:]).copy()
+    bp[:, 2:3 * N:3, 1] *= rng.uniform(0.9, 1.3, (B, 1))                      # thrust bound per problem
+    bp[:, 3 * N, 2:5] = 0.5 * rng.standard_normal((B, 3))                     # terminal position per problem
+    n = 9 * N + 6
+    prob = dict(prob, block_par=bp, z0=0.1 * rng.standard_normal((B, n)), u0=0.01 * rng.standard_normal((B, n)))
+    got = solver.scp_solve(prob, scp, opts)
+    ref = scp_ocp.scp_solve(prob, scp, opts)
+    _assert_scp_equal(got, ref)
+    assert (got[3]["scp_status"] == 0).all()
+
+
+@pytest.mark.gpu
 def test_scp_max_pass_and_quadratic_cost(solver, P):
     """max_pass cuts the loop (status 1, same bits as the oracle cut at the same pass); per-problem Q, R and a linear
     cost q travel through the passes."""
