@@ -4,6 +4,8 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as graft
 pkg = graft.load_pkg()
+if os.environ.get("ADMMB_LIB"):          # developer build of the library
+    pkg._lib.LIB_PATH = os.path.abspath(os.environ["ADMMB_LIB"])
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 max_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 prec = sys.argv[3] if len(sys.argv) > 3 else "tf32"
