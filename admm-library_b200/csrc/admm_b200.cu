@@ -575,6 +575,7 @@ void Shard::scp_solve(const admmb_scp *sc, const admmb_opts *op, admmb_result *r
     C.dt = sc->T / (double)C.substeps;
     C.hdt = 0.5 * C.dt;
     C.dt6 = C.dt / 6.0;
+    C.impulsive = sc->control == ADMMB_SCP_CTRL_IMPULSIVE;
     scp_max_pass = sc->max_pass;
     scp_lin_ms = 0.0;
     scp_xref.alloc((size_t)n * ld);
@@ -1376,6 +1377,8 @@ int admmb_scp_solve(admmb_handle h, const admmb_problem *pb, const admmb_scp *sc
     if (sc->substeps < 0 || sc->substeps > 4096) return fail(h, ADMMB_E_BADARG, "scp: substeps out of range");
     if (sc->max_pass < 1 || sc->max_pass > 1000) return fail(h, ADMMB_E_BADARG, "scp: max_pass must be in 1 .. 1000");
     if (!(sc->tol_abs >= 0.0) || !(sc->tol_rel >= 0.0)) return fail(h, ADMMB_E_BADARG, "scp: tolerances must be >= 0");
+    if (sc->control != ADMMB_SCP_CTRL_ZOH && sc->control != ADMMB_SCP_CTRL_IMPULSIVE)
+        return fail(h, ADMMB_E_BADARG, "scp: control must be an ADMMB_SCP_CTRL_* code");
     if (op->adapt_rho || op->history || pb->rho0)
         return fail(h, ADMMB_E_BADARG, "scp: adaptive / per-problem rho and the per-iteration history are not carried across passes");
     if (op->xupdate == ADMMB_XUPDATE_DENSE || op->precision != ADMMB_PREC_FP64)

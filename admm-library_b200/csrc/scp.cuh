@@ -21,6 +21,7 @@ namespace admmb {
 struct ScpConst {
     double R0, twoR0, R0sq, n2, tn, dt, hdt, dt6;
     int substeps;
+    int impulsive;       // the control is a velocity increment at the start of the stage, followed by a coast
 };
 
 struct ScpCoef {
@@ -74,30 +75,39 @@ __device__ inline void scp_linearise_stage(const ScpConst &C, const double *sr, 
                                            size_t ld)
 {
     double cacc[6];
-    for (int j = 0; j < 9; ++j) {
+    // impulsive control (oracle/scp_ocp.py _linearise_stage_impulsive): s+ = F(s + [0; dv]) with F the coast, so A = dF/ds at the
+    // post-impulse state, B = A[:, 3:6] (six columns instead of nine), c = F - A sr - B dv
+    const bool imp = C.impulsive != 0;
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    const double *af = imp ? zero3 : ar;                 // the acceleration the RK4 sees
+    double s_in[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s_in[i] = (imp && i >= 3) ? sr[i] + ar[i - 3] : sr[i];
+    const int ncol = imp ? 6 : 9;
+    for (int j = 0; j < ncol; ++j) {
         const int fr = j >= 6 ? j - 3 : -1;
         double s[6], y[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { s[i] = sr[i]; y[i] = (i == j) ? 1.0 : 0.0; }
+        for (int i = 0; i < 6; ++i) { s[i] = s_in[i]; y[i] = (i == j) ? 1.0 : 0.0; }
         for (int ss = 0; ss < C.substeps; ++ss) {
             double k[6], l[6], ts[6], ty[6], as[6], ay[6];
             ScpCoef cf = scp_coeffs(s, C);
-            scp_f_state(cf, s, ar, C.tn, k);
+            scp_f_state(cf, s, af, C.tn, k);
             scp_f_col(cf, s, y, C.tn, fr, l);
 #pragma unroll
             for (int i = 0; i < 6; ++i) { as[i] = k[i]; ay[i] = l[i]; ts[i] = s[i] + C.hdt * k[i]; ty[i] = y[i] + C.hdt * l[i]; }
             cf = scp_coeffs(ts, C);
-            scp_f_state(cf, ts, ar, C.tn, k);
+            scp_f_state(cf, ts, af, C.tn, k);
             scp_f_col(cf, ts, ty, C.tn, fr, l);
 #pragma unroll
             for (int i = 0; i < 6; ++i) { as[i] = as[i] + 2.0 * k[i]; ay[i] = ay[i] + 2.0 * l[i]; ts[i] = s[i] + C.hdt * k[i]; ty[i] = y[i] + C.hdt * l[i]; }
             cf = scp_coeffs(ts, C);
-            scp_f_state(cf, ts, ar, C.tn, k);
+            scp_f_state(cf, ts, af, C.tn, k);
             scp_f_col(cf, ts, ty, C.tn, fr, l);
 #pragma unroll
             for (int i = 0; i < 6; ++i) { as[i] = as[i] + 2.0 * k[i]; ay[i] = ay[i] + 2.0 * l[i]; ts[i] = s[i] + C.dt * k[i]; ty[i] = y[i] + C.dt * l[i]; }
             cf = scp_coeffs(ts, C);
-            scp_f_state(cf, ts, ar, C.tn, k);
+            scp_f_state(cf, ts, af, C.tn, k);
             scp_f_col(cf, ts, ty, C.tn, fr, l);
 #pragma unroll
             for (int i = 0; i < 6; ++i) { s[i] = s[i] + C.dt6 * (as[i] + k[i]); y[i] = y[i] + C.dt6 * (ay[i] + l[i]); }
@@ -109,6 +119,15 @@ __device__ inline void scp_linearise_stage(const ScpConst &C, const double *sr, 
             if (j == 0) { cacc[i] = s[i]; F[i] = s[i]; }
             out[(size_t)i * ld] = y[i];
             cacc[i] = cacc[i] - y[i] * v;
+        }
+        if (imp && j >= 3) {                           // the same column is B's column j - 3
+            double *outb = Bk + (size_t)(6 * (j - 3)) * ld;
+            const double vb = ar[j - 3];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                outb[(size_t)i * ld] = y[i];
+                cacc[i] = cacc[i] - y[i] * vb;
+            }
         }
     }
 #pragma unroll

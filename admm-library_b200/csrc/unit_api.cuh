@@ -236,6 +236,7 @@ int admmb_k_scp_linearise(admmb_handle h, int32_t N, int64_t batch, const admmb_
         C.R0 = sc->R0; C.twoR0 = 2.0 * sc->R0; C.R0sq = sc->R0 * sc->R0;
         C.n2 = nmm * nmm; C.tn = 2.0 * nmm;
         C.dt = sc->T / (double)C.substeps; C.hdt = 0.5 * C.dt; C.dt6 = C.dt / 6.0;
+        C.impulsive = sc->control == ADMMB_SCP_CTRL_IMPULSIVE;
         const unsigned gb = (unsigned)((batch + 127) / 128);
         if (shoot) k_scp_shoot<<<gb, 128, 0, U.s.stream>>>(C, batch, N, ld, ds0.p, dx.p, dA.p, dB.p, dc.p);
         else k_scp_linearise<<<dim3(gb, (unsigned)N), 128, 0, U.s.stream>>>(C, batch, N, ld, nullptr, dx.p, dA.p, dB.p, dc.p);

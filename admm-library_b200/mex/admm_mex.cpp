@@ -172,6 +172,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         sc.max_pass = (int32_t)opt_scalar(S, "max_pass", 10);
         sc.tol_abs = opt_scalar(S, "tol_abs", 0.0);
         sc.tol_rel = opt_scalar(S, "tol_rel", 1e-6);
+        static const char *const ctrls[] = {"zoh", "impulsive"};
+        sc.control = opt_enum(S, "control", ctrls, 2, ADMMB_SCP_CTRL_ZOH);
     }
 
     // ---- handle: created once, kept across calls (CUDA context, device buffers, worker threads)

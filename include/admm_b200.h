@@ -206,6 +206,10 @@ enum {
     ADMMB_SCP_NL_CIRCULAR = 1    /* deputy about a chief on a circular orbit of radius R0: LVLH frame, full two-body
                                     gravity, zero-order-hold thrust acceleration (linearised at r = 0: Clohessy-Wiltshire) */
 };
+enum {
+    ADMMB_SCP_CTRL_ZOH = 0,       /* thrust acceleration held over the stage (low-thrust transfers, configs 3 / 4)   */
+    ADMMB_SCP_CTRL_IMPULSIVE = 1  /* velocity increment at the start of the stage, then a coast (configs 1, 2, 5)    */
+};
 typedef struct admmb_scp {
     int32_t model;               /* ADMMB_SCP_*                                                  */
     int32_t substeps;            /* RK4 steps per stage (0 = 8)                                  */
@@ -214,6 +218,7 @@ typedef struct admmb_scp {
     double R0;                   /* radius of the chief's orbit, in the problem's length unit    */
     int32_t max_pass;            /* linearise + solve passes at most (>= 1)                      */
     double tol_abs, tol_rel;     /* per-problem stop: max|x - x_ref| <= tol_abs + tol_rel max|x|, last solve converged */
+    int32_t control;             /* ADMMB_SCP_CTRL_*: how the three controls of a stage act                          */
 } admmb_scp;
 /* per-problem SCP outputs; caller-allocated, any pointer may be NULL */
 typedef struct admmb_scp_result {

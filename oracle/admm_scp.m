@@ -8,7 +8,8 @@ function [x, z, u, hist] = admm_scp(prob, opts, scp)
 %
 %   prob: N, s0 [6 x Bsz], block_type, block_par, optional q / per-problem Q, R  (A, B, c are produced here)
 %   scp : T (stage length), R0 (radius of the chief's circular orbit), nmm (mean motion, default 1),
-%         substeps (RK4 steps per stage, default 8), max_pass, tol_abs, tol_rel
+%         substeps (RK4 steps per stage, default 8), max_pass, tol_abs, tol_rel,
+%         control ('zoh' thrust acceleration held over the stage (default) | 'impulsive' velocity increment + coast)
 %
 %   model: deputy about a chief on a circular orbit, LVLH frame (x radial, y along-track, z cross-track),
 %          mu = n^2 R0^3, full two-body gravity, zero-order-hold thrust acceleration a:
@@ -67,6 +68,20 @@ end
 
 function [F, A, B, c] = stage(sr, ar, scp)
 % RK4 of the state and, column by column, of [Phi | Gamma]; sr [6 x B], ar [3 x B]
+    if isfield(scp, 'control') && strcmp(scp.control, 'impulsive')
+        % velocity increment at the start of the stage, then a coast: A = dF/ds at the post-impulse state, B = A(:,4:6)
+        sin = sr;  sin(4:6,:) = sr(4:6,:) + ar;
+        coast = scp;  coast.control = 'zoh';
+        [F, A, ~, ~] = stage(sin, zeros(3, size(sr,2)), coast);
+        B = A(:,4:6,1,:);
+        c = F;
+        for j = 1:6
+            y = squeeze(A(:,j,1,:));  if size(sr,2) == 1, y = y(:); end
+            c = c - y .* sr(j,:);
+            if j > 3, c = c - y .* ar(j-3,:); end
+        end
+        return;
+    end
     Bsz = size(sr, 2);  n = scp.nmm;  R0 = scp.R0;  n2 = n*n;  tn = 2*n;
     dt = scp.T / scp.substeps;  hdt = 0.5*dt;  dt6 = dt/6;
     A = zeros(6,6,1,Bsz); B = zeros(6,3,1,Bsz);

@@ -6,7 +6,9 @@ same arithmetic, so that the device result can be compared BIT FOR BIT, pass by 
 
   * the nonlinear model: relative motion of a deputy about a chief on a circular orbit of radius R0 (LVLH frame, x
     radial, y along-track, z cross-track, mean motion n, mu = n^2 R0^3), full two-body gravity, zero-order-hold
-    thrust acceleration a.  Its linearisation at r = 0 is the Clohessy-Wiltshire model of configs 1-3;
+    thrust acceleration a (scp["control"] = "zoh") or a velocity increment at the start of each stage followed by a
+    coast ("impulsive": the fuel-optimal impulsive rendezvous of configs 1, 2, 5).  Its linearisation at r = 0 is the
+    Clohessy-Wiltshire model of configs 1-3;
   * per pass, per stage: classical RK4 (`substeps` per stage) of the state together with its variational equations
     (one column of [Phi | Gamma] at a time, as the device does) about the reference (s_ref_k, a_ref_k):
         A_k = dF/ds, B_k = dF/da, c_k = F(s_ref_k, a_ref_k) - A_k s_ref_k - B_k a_ref_k;
@@ -71,8 +73,11 @@ def _f_col(J, y, tn, forced_row):
     return dy
 
 
-def linearise_stage(s_ref, a_ref, T, substeps, nmm, R0):
-    """One stage about (s_ref [B,6], a_ref [B,3]) -> F [B,6], A [B,6,6], Bm [B,6,3], c [B,6]."""
+def linearise_stage(s_ref, a_ref, T, substeps, nmm, R0, impulsive=False):
+    """One stage about (s_ref [B,6], a_ref [B,3]) -> F [B,6], A [B,6,6], Bm [B,6,3], c [B,6].
+    impulsive: the control is a velocity increment applied at the start of the stage, followed by a coast."""
+    if impulsive:
+        return _linearise_stage_impulsive(s_ref, a_ref, T, substeps, nmm, R0)
     Bsz = s_ref.shape[0]
     n = np.float64(nmm)
     R0 = np.float64(R0)
@@ -126,6 +131,65 @@ def linearise_stage(s_ref, a_ref, T, substeps, nmm, R0):
     return F, A, Bm, np.stack(c, axis=1)
 
 
+def _linearise_stage_impulsive(s_ref, a_ref, T, substeps, nmm, R0):
+    """s+ = F(s + [0; dv]) with F the coast over T: A = dF/ds at the post-impulse state, B = A[:, 3:6],
+    c = F - A s_ref - B dv_ref, subtracted column by column (state entry j, then -- for the velocity columns -- impulse
+    entry j - 3), as the device does."""
+    Bsz = s_ref.shape[0]
+    n = np.float64(nmm)
+    R0 = np.float64(R0)
+    n2 = n * n
+    tn = 2.0 * n
+    dt = np.float64(T) / np.float64(substeps)
+    hdt = 0.5 * dt
+    dt6 = dt / 6.0
+    s = [s_ref[:, i].copy() for i in range(3)] + [s_ref[:, 3 + i] + a_ref[:, i] for i in range(3)]
+    a = [np.zeros(Bsz) for _ in range(3)]
+    cols = []
+    for j in range(6):
+        y = [np.zeros(Bsz) for _ in range(6)]
+        y[j] = np.ones(Bsz)
+        cols.append(y)
+    for _ in range(substeps):
+        c1 = _coeffs(s, R0, n2)
+        k1 = _f_state(c1, s, a, tn)
+        s2 = [s[i] + hdt * k1[i] for i in range(6)]
+        c2 = _coeffs(s2, R0, n2)
+        k2 = _f_state(c2, s2, a, tn)
+        s3 = [s[i] + hdt * k2[i] for i in range(6)]
+        c3 = _coeffs(s3, R0, n2)
+        k3 = _f_state(c3, s3, a, tn)
+        s4 = [s[i] + dt * k3[i] for i in range(6)]
+        c4 = _coeffs(s4, R0, n2)
+        k4 = _f_state(c4, s4, a, tn)
+        J1, J2, J3, J4 = _jac(c1, s), _jac(c2, s2), _jac(c3, s3), _jac(c4, s4)
+        for j in range(6):
+            y = cols[j]
+            l1 = _f_col(J1, y, tn, -1)
+            l2 = _f_col(J2, [y[i] + hdt * l1[i] for i in range(6)], tn, -1)
+            l3 = _f_col(J3, [y[i] + hdt * l2[i] for i in range(6)], tn, -1)
+            l4 = _f_col(J4, [y[i] + dt * l3[i] for i in range(6)], tn, -1)
+            cols[j] = [y[i] + dt6 * (((l1[i] + 2.0 * l2[i]) + 2.0 * l3[i]) + l4[i]) for i in range(6)]
+        s = [s[i] + dt6 * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]) for i in range(6)]
+    F = np.stack(s, axis=1)
+    A = np.zeros((Bsz, 6, 6))
+    Bm = np.zeros((Bsz, 6, 3))
+    c = [s[i].copy() for i in range(6)]
+    for j in range(6):
+        for i in range(6):
+            A[:, i, j] = cols[j][i]
+            c[i] = c[i] - cols[j][i] * s_ref[:, j]
+        if j >= 3:
+            for i in range(6):
+                Bm[:, i, j - 3] = cols[j][i]
+                c[i] = c[i] - cols[j][i] * a_ref[:, j - 3]
+    return F, A, Bm, np.stack(c, axis=1)
+
+
+def _impulsive(scp) -> bool:
+    return scp.get("control", "zoh") == "impulsive"
+
+
 def linearise(xref, N, scp):
     """Every stage about the reference trajectory xref [B, 9N+6] -> A [B,N,6,6], Bm [B,N,6,3], c [B,N,6]."""
     Bsz = xref.shape[0]
@@ -135,7 +199,7 @@ def linearise(xref, N, scp):
     for k in range(N):
         _, A[:, k], Bm[:, k], c[:, k] = linearise_stage(xref[:, 9 * k:9 * k + 6], xref[:, 9 * k + 6:9 * k + 9],
                                                          scp["T"], scp.get("substeps", 8), scp.get("nmm", 1.0),
-                                                         scp["R0"])
+                                                         scp["R0"], _impulsive(scp))
     return A, Bm, c
 
 
@@ -153,14 +217,14 @@ def shoot(s0, controls, N, scp):
         xref[:, 9 * k:9 * k + 6] = s
         xref[:, 9 * k + 6:9 * k + 9] = a
         s, A[:, k], Bm[:, k], c[:, k] = linearise_stage(s, a, scp["T"], scp.get("substeps", 8),
-                                                         scp.get("nmm", 1.0), scp["R0"])
+                                                         scp.get("nmm", 1.0), scp["R0"], _impulsive(scp))
     xref[:, 9 * N:] = s
     return xref, A, Bm, c
 
 
 def scp_solve(prob: dict, scp: dict, opts: dict, solve=None):
     """SCP on a batch.  prob: N, s0 [B,6], block_type, block_par, optional q / Q / R as for the ADMM oracle (A, B, c
-    are produced here).  scp: dict(T, R0, nmm=1, substeps=8, max_pass, tol_abs, tol_rel).
+    are produced here).  scp: dict(T, R0, nmm=1, substeps=8, max_pass, tol_abs, tol_rel, control="zoh" | "impulsive").
     -> x, z, u [B,n], info dict(passes, scp_status (0 converged, 1 max_pass), step, iters_total, iters, status,
     hist_step [B,max_pass] (NaN after a problem's exit))."""
     if solve is None:

@@ -44,14 +44,18 @@ def test_struct_layouts_match_the_c_compiler(pkg, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "admm_b200.h"\nint main(void){'
                    'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(admmb_problem), sizeof(admmb_opts), sizeof(admmb_result),'
-                   'offsetof(admmb_problem, block_par), offsetof(admmb_opts, xupdate), offsetof(admmb_result, stats));return 0;}')
+                   'offsetof(admmb_problem, block_par), offsetof(admmb_opts, xupdate), offsetof(admmb_result, stats));'
+                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(admmb_generator), sizeof(admmb_scp), sizeof(admmb_scp_result),'
+                   'offsetof(admmb_generator, e), offsetof(admmb_scp, control), offsetof(admmb_scp_result, stats));return 0;}')
     exe = tmp_path / "sz"
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     L = pkg._lib
     want = [C.sizeof(L.Problem), C.sizeof(L.Opts), C.sizeof(L.Result), L.Problem.block_par.offset,
-            L.Opts.xupdate.offset, L.Result.stats.offset]
+            L.Opts.xupdate.offset, L.Result.stats.offset,
+            C.sizeof(L.Generator), C.sizeof(L.Scp), C.sizeof(L.ScpResult), L.Generator.e.offset, L.Scp.control.offset,
+            L.ScpResult.stats.offset]
     assert got == want
 
 

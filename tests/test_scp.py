@@ -107,15 +107,54 @@ def test_scp_controls_reach_the_target_in_the_nonlinear_dynamics(P, cpu_oracle):
     assert miss_cw.min() >= 100.0 * miss.max()
 
 
+def _fixture_workload(P, g):
+    make = P.scp_nonlinear_impulsive if str(g["control"]) == "impulsive" else P.scp_nonlinear_rendezvous
+    return make(int(g["batch"]), int(g["N"]), seed=int(g["seed"]), scale=float(g["scale"]), substeps=int(g["substeps"]))
+
+
 def test_scp_golden_fixtures_exist():
-    assert len(SCP_GOLDEN) >= 2
+    assert len(SCP_GOLDEN) >= 3
+
+
+def test_impulsive_stage_is_a_coast_after_the_velocity_increment():
+    """control = "impulsive": s+ = F(s + [0; dv]); A = dF/ds at the post-impulse state, B = A[:, 3:6]; checked against
+    solve_ivp of the coast and finite differences in dv."""
+    from scipy.integrate import solve_ivp
+    s, dv = _case(B=4, seed=11)
+    T, R0, n, sub = 0.3, 7000.0, 1.0, 48
+    F, A, Bm, c = scp_ocp.linearise_stage(s, dv, T, sub, n, R0, impulsive=True)
+    assert np.array_equal(Bm, A[:, :, 3:6])
+    for i in range(s.shape[0]):
+        s_in = s[i].copy(); s_in[3:] += dv[i]
+        sol = solve_ivp(_nl_rhs, (0.0, T), s_in, args=(np.zeros(3), n, R0), rtol=1e-12, atol=1e-12, method="DOP853")
+        assert np.abs(F[i] - sol.y[:, -1]).max() <= 1e-8 * (1.0 + np.abs(F[i]).max())
+    h = 1e-4
+    for j in range(3):
+        e = np.zeros(3); e[j] = h
+        Fp, *_ = scp_ocp.linearise_stage(s, dv + e, T, sub, n, R0, impulsive=True)
+        Fm, *_ = scp_ocp.linearise_stage(s, dv - e, T, sub, n, R0, impulsive=True)
+        assert np.abs((Fp - Fm) / (2 * h) - Bm[:, :, j]).max() <= 1e-7
+    lin = np.einsum("bij,bj->bi", A, s) + np.einsum("bij,bj->bi", Bm, dv) + c
+    assert np.abs(lin - F).max() <= 1e-9 * np.abs(F).max()
+
+
+def test_scp_impulsive_controls_reach_the_target(P):
+    B, N = 4, 12
+    prob, scp, opts = P.scp_nonlinear_impulsive(B, N, seed=9, scale=30.0)
+    x, z, u, info = scp_ocp.scp_solve(prob, scp, opts)
+    assert (info["scp_status"] == 0).all() and (info["status"] == 0).all()
+    dv = z[:, :9 * N].reshape(B, N, 9)[:, :, 6:9]
+    s = prob["s0"].copy()
+    for k in range(N):
+        s, *_ = scp_ocp.linearise_stage(s, dv[:, k], scp["T"], scp["substeps"], 1.0, scp["R0"], impulsive=True)
+    assert np.abs(s).max() <= 5e-3
+    assert np.abs(dv).max() <= prob["block_par"][0, 2, 5] + 1e-9          # box on every increment
 
 
 @pytest.mark.parametrize("path", SCP_GOLDEN, ids=[os.path.basename(p) for p in SCP_GOLDEN])
 def test_scp_oracle_reproduces_golden_fixtures(P, path):
     g = np.load(path)
-    prob, scp, opts = P.scp_nonlinear_rendezvous(int(g["batch"]), int(g["N"]), seed=int(g["seed"]), scale=float(g["scale"]),
-                                                 substeps=int(g["substeps"]))
+    prob, scp, opts = _fixture_workload(P, g)
     assert np.array_equal(prob["s0"], g["s0"])
     xref0, A0, B0, c0 = scp_ocp.shoot(prob["s0"], None, int(g["N"]), scp)
     for a, k in ((xref0, "xref0"), (A0, "A0"), (B0, "B0"), (c0, "c0")):
@@ -177,11 +216,24 @@ def test_scp_linearise_kernels_bit_identical(solver, B, N, sub):
 
 
 @pytest.mark.gpu
+def test_scp_impulsive_linearise_and_solve_bit_identical(solver, P):
+    rng = np.random.Generator(np.random.PCG64(77))
+    B, N = 37, 9
+    scp = dict(T=2.0 * np.pi / N, R0=6900.0, nmm=1.0, substeps=3, control="impulsive")
+    xref = 40.0 * rng.standard_normal((B, 9 * N + 6))
+    A, Bm, c, _ = solver.k_scp_linearise(N, scp, xref)
+    Ao, Bo, co = scp_ocp.linearise(xref, N, scp)
+    assert np.array_equal(A, Ao) and np.array_equal(Bm, Bo) and np.array_equal(c, co)
+    assert np.array_equal(Bm, A[:, :, :, 3:6])
+    prob, scp, opts = P.scp_nonlinear_impulsive(B, 12, seed=9, scale=30.0, substeps=3)
+    _assert_scp_equal(solver.scp_solve(prob, scp, opts), scp_ocp.scp_solve(prob, scp, opts))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("path", SCP_GOLDEN, ids=[os.path.basename(p) for p in SCP_GOLDEN])
 def test_scp_gpu_reproduces_golden_fixtures(solver, P, path):
     g = np.load(path)
-    prob, scp, opts = P.scp_nonlinear_rendezvous(int(g["batch"]), int(g["N"]), seed=int(g["seed"]), scale=float(g["scale"]),
-                                                 substeps=int(g["substeps"]))
+    prob, scp, opts = _fixture_workload(P, g)
     x, z, u, info = solver.scp_solve(prob, scp, opts)
     ref = (g["x"], g["z"], g["u"], {k: g[k] for k in ("passes", "hist_step", "scp_status", "iters_total", "iters", "status", "step")})
     _assert_scp_equal((x, z, u, info), ref)
