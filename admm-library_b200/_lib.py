@@ -38,7 +38,7 @@ class Generator(C.Structure):
 class Scp(C.Structure):
     _fields_ = [("model", C.c_int32), ("substeps", C.c_int32), ("T", C.c_double), ("nmm", C.c_double),
                 ("R0", C.c_double), ("max_pass", C.c_int32), ("tol_abs", C.c_double), ("tol_rel", C.c_double),
-                ("control", C.c_int32)]
+                ("control", C.c_int32), ("e", c_dp), ("theta0", c_dp)]
 
 
 class ScpResult(C.Structure):

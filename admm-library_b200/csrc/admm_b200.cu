@@ -194,7 +194,7 @@ struct Shard {
     // sequential convex programming on the resident batch (scp.cuh)
     bool scp_upload = false;          // set around upload(): per-problem model + affine term, produced on the device
     const int *run_active = nullptr;  // run(): problems with a zero entry keep the state of their last solve
-    DevBuf<double> scp_xref, scp_step, scp_hist;
+    DevBuf<double> scp_xref, scp_step, scp_hist, scp_e, scp_th0, scp_theta;   // scp_theta [N][ld]: true anomaly at every stage start
     DevBuf<int> scp_active, scp_passes, scp_status, scp_count;
     DevBuf<long long> scp_iters;
     int scp_max_pass = 0;
@@ -544,10 +544,11 @@ void Shard::scp_linearise(const ScpConst &C, bool shoot)
     CK(cudaEventRecord(a, stream));
     const unsigned gb = (unsigned)((batch + 127) / 128);
     if (shoot) {
-        k_scp_shoot<<<gb, 128, 0, stream>>>(C, batch, N, ld, s0.p, scp_xref.p, rawA.p, rawB.p, rawc.p);
+        k_scp_shoot<<<gb, 128, 0, stream>>>(C, batch, N, ld, s0.p, scp_xref.p, rawA.p, rawB.p, rawc.p, scp_e.p, scp_theta.p);
     } else {
         dim3 grid(gb, (unsigned)N);
-        k_scp_linearise<<<grid, 128, 0, stream>>>(C, batch, N, ld, scp_active.p, scp_xref.p, rawA.p, rawB.p, rawc.p);
+        k_scp_linearise<<<grid, 128, 0, stream>>>(C, batch, N, ld, scp_active.p, scp_xref.p, rawA.p, rawB.p, rawc.p, scp_e.p,
+                                                  scp_theta.p);
     }
     ++launches;
     cudaError_t e = cudaGetLastError();
@@ -576,6 +577,18 @@ void Shard::scp_solve(const admmb_scp *sc, const admmb_opts *op, admmb_result *r
     C.hdt = 0.5 * C.dt;
     C.dt6 = C.dt / 6.0;
     C.impulsive = sc->control == ADMMB_SCP_CTRL_IMPULSIVE;
+    C.elliptic = sc->model == ADMMB_SCP_NL_ELLIPTIC;
+    if (C.elliptic) {   // the orbit's own clock: true anomaly at the start of every stage, once per solve
+        scp_e.alloc(ld);
+        scp_th0.alloc(ld);
+        scp_theta.alloc((size_t)N * ld);
+        CK(cudaMemcpyAsync(scp_e.p, sc->e + p_begin, sizeof(double) * batch, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(scp_th0.p, sc->theta0 + p_begin, sizeof(double) * batch, cudaMemcpyHostToDevice, stream));
+        k_scp_theta<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(batch, N, ld, C.dt, C.hdt, C.dt6, C.substeps, scp_e.p,
+                                                                         scp_th0.p, scp_theta.p);
+        ++launches;
+        CK(cudaGetLastError());
+    }
     scp_max_pass = sc->max_pass;
     scp_lin_ms = 0.0;
     scp_xref.alloc((size_t)n * ld);
@@ -1370,7 +1383,15 @@ int admmb_scp_solve(admmb_handle h, const admmb_problem *pb, const admmb_scp *sc
     int rc = validate(h, pb, op, nullptr, true);
     if (rc != ADMMB_OK) return rc;
     if (!sc) return fail(h, ADMMB_E_BADARG, "null scp");
-    if (sc->model != ADMMB_SCP_NL_CIRCULAR) return fail(h, ADMMB_E_BADARG, "scp: model must be an ADMMB_SCP_* code");
+    if (sc->model != ADMMB_SCP_NL_CIRCULAR && sc->model != ADMMB_SCP_NL_ELLIPTIC)
+        return fail(h, ADMMB_E_BADARG, "scp: model must be an ADMMB_SCP_* code");
+    if (sc->model == ADMMB_SCP_NL_ELLIPTIC) {
+        if (!sc->e || !sc->theta0) return fail(h, ADMMB_E_BADARG, "scp: e and theta0 are required for ADMMB_SCP_NL_ELLIPTIC");
+        if (sc->nmm != 0.0 && sc->nmm != 1.0) return fail(h, ADMMB_E_BADARG, "scp: the elliptic model uses the time unit 1 / mean motion (nmm = 1)");
+        for (int64_t i = 0; i < pb->batch; ++i)
+            if (!(sc->e[i] >= 0.0 && sc->e[i] < 1.0) || !std::isfinite(sc->theta0[i]) || std::fabs(sc->theta0[i]) > 1.0e3)
+                return fail(h, ADMMB_E_BADARG, "scp: problem %lld needs 0 <= e < 1 and |theta0| <= 1000", (long long)i);
+    }
     if (!(sc->T > 0.0) || !std::isfinite(sc->T)) return fail(h, ADMMB_E_BADARG, "scp: stage length T must be > 0");
     if (!(sc->R0 > 0.0) || !std::isfinite(sc->R0)) return fail(h, ADMMB_E_BADARG, "scp: orbit radius R0 must be > 0");
     if (!(sc->nmm >= 0.0) || !std::isfinite(sc->nmm)) return fail(h, ADMMB_E_BADARG, "scp: mean motion must be > 0 (0 = 1)");

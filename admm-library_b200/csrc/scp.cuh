@@ -22,6 +22,7 @@ struct ScpConst {
     double R0, twoR0, R0sq, n2, tn, dt, hdt, dt6;
     int substeps;
     int impulsive;       // the control is a velocity increment at the start of the stage, followed by a coast
+    int elliptic;        // model ADMMB_SCP_NL_ELLIPTIC: R0 is the semi-major axis, time unit 1 / mean motion
 };
 
 struct ScpCoef {
@@ -134,10 +135,160 @@ __device__ inline void scp_linearise_stage(const ScpConst &C, const double *sr, 
     for (int i = 0; i < 6; ++i) ck[(size_t)i * ld] = cacc[i];
 }
 
+// ---- model ADMMB_SCP_NL_ELLIPTIC (oracle/scp_ocp.py _ell_*): the chief is on a Kepler orbit of eccentricity e; the LVLH
+// frame's rotation rate w, its derivative wd, K = mu / R^3 and the chief radius R follow the true anomaly, which is
+// integrated by the same RK4 (theta' = w).  Linearised at r = 0 this is config 4's model (generators.cuh k_gen_elliptic).
+struct EllOrb {
+    double w, wd, K, R;
+};
+__device__ __forceinline__ EllOrb scp_ell_coef(double th, double e, double p, double h, double a)
+{
+    double st, ct;
+    det_sincos(th, st, ct);
+    const double one_ec = 1.0 + e * ct;
+    const double r = p / one_ec;
+    EllOrb o;
+    o.w = h / (r * r);
+    const double rdot = (e * st) / h;
+    o.wd = ((-2.0 * o.w) * rdot) / r;
+    o.K = 1.0 / ((r * r) * r);
+    o.R = a * r;
+    return o;
+}
+struct EllGrav {
+    double rx, Kg, m;
+};
+__device__ __forceinline__ EllGrav scp_ell_grav(const EllOrb &o, const double *s)
+{
+    EllGrav g;
+    g.rx = o.R + s[0];
+    const double q = ((((2.0 * o.R) * s[0] + s[0] * s[0]) + s[1] * s[1]) + s[2] * s[2]) / (o.R * o.R);
+    const double w_ = 1.0 + q;
+    const double w32 = w_ * sqrt(w_);
+    const double gf = (q * ((3.0 + 3.0 * q) + q * q)) / (w32 * (1.0 + w32));
+    g.Kg = o.K * gf;
+    g.m = (3.0 * o.K) / (((o.R * o.R) * w_) * w32);
+    return g;
+}
+__device__ __forceinline__ void scp_ell_f(const EllOrb &o, const EllGrav &g, const double *s, const double *a, const double *y,
+                                          int forced_row, double *ds, double *dy)
+{
+    const double tw = 2.0 * o.w;
+    const double wK = o.w * o.w - o.K;
+    ds[0] = s[3];
+    ds[1] = s[4];
+    ds[2] = s[5];
+    ds[3] = ((((tw * s[4]) + (o.wd * s[1])) + (wK * s[0])) + (g.Kg * g.rx)) + a[0];
+    ds[4] = (((((-tw) * s[3]) + ((-o.wd) * s[0])) + (wK * s[1])) + (g.Kg * s[1])) + a[1];
+    ds[5] = (((-o.K) * s[2]) + (g.Kg * s[2])) + a[2];
+    const double j30 = (wK + g.Kg) + g.m * (g.rx * g.rx), j31 = o.wd + g.m * (g.rx * s[1]), j32 = g.m * (g.rx * s[2]);
+    const double j40 = (-o.wd) + g.m * (g.rx * s[1]), j41 = (wK + g.Kg) + g.m * (s[1] * s[1]), j42 = g.m * (s[1] * s[2]);
+    const double j50 = g.m * (g.rx * s[2]), j51 = g.m * (s[1] * s[2]), j52 = ((-o.K) + g.Kg) + g.m * (s[2] * s[2]);
+    dy[0] = y[3];
+    dy[1] = y[4];
+    dy[2] = y[5];
+    dy[3] = (((j30 * y[0]) + (j31 * y[1])) + (j32 * y[2])) + tw * y[4];
+    dy[4] = (((j40 * y[0]) + (j41 * y[1])) + (j42 * y[2])) + (-tw) * y[3];
+    dy[5] = ((j50 * y[0]) + (j51 * y[1])) + (j52 * y[2]);
+    if (forced_row == 3) dy[3] = dy[3] + 1.0;
+    if (forced_row == 4) dy[4] = dy[4] + 1.0;
+    if (forced_row == 5) dy[5] = dy[5] + 1.0;
+}
+
+// oracle/scp_ocp.py linearise_stage_elliptic; th_k: true anomaly at the start of the stage, e: this problem's eccentricity
+__device__ inline void scp_linearise_stage_ell(const ScpConst &C, double e, double th_k, const double *sr, const double *ar,
+                                               double *F, double *__restrict__ Ak, double *__restrict__ Bk,
+                                               double *__restrict__ ck, size_t ld)
+{
+    double cacc[6];
+    const double p = 1.0 - e * e;
+    const double h = sqrt(p);
+    const bool imp = C.impulsive != 0;
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    const double *af = imp ? zero3 : ar;
+    double s_in[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s_in[i] = (imp && i >= 3) ? sr[i] + ar[i - 3] : sr[i];
+    const int ncol = imp ? 6 : 9;
+    for (int j = 0; j < ncol; ++j) {
+        const int fr = j >= 6 ? j - 3 : -1;
+        double s[6], y[6];
+        double th = th_k;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s[i] = s_in[i]; y[i] = (i == j) ? 1.0 : 0.0; }
+        for (int ss = 0; ss < C.substeps; ++ss) {
+            double k[6], l[6], ts[6], ty[6], as[6], ay[6];
+            const EllOrb o1 = scp_ell_coef(th, e, p, h, C.R0);
+            const EllOrb o2 = scp_ell_coef(th + C.hdt * o1.w, e, p, h, C.R0);
+            const EllOrb o3 = scp_ell_coef(th + C.hdt * o2.w, e, p, h, C.R0);
+            const EllOrb o4 = scp_ell_coef(th + C.dt * o3.w, e, p, h, C.R0);
+            EllGrav g = scp_ell_grav(o1, s);
+            scp_ell_f(o1, g, s, af, y, fr, k, l);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { as[i] = k[i]; ay[i] = l[i]; ts[i] = s[i] + C.hdt * k[i]; ty[i] = y[i] + C.hdt * l[i]; }
+            g = scp_ell_grav(o2, ts);
+            scp_ell_f(o2, g, ts, af, ty, fr, k, l);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { as[i] = as[i] + 2.0 * k[i]; ay[i] = ay[i] + 2.0 * l[i]; ts[i] = s[i] + C.hdt * k[i]; ty[i] = y[i] + C.hdt * l[i]; }
+            g = scp_ell_grav(o3, ts);
+            scp_ell_f(o3, g, ts, af, ty, fr, k, l);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { as[i] = as[i] + 2.0 * k[i]; ay[i] = ay[i] + 2.0 * l[i]; ts[i] = s[i] + C.dt * k[i]; ty[i] = y[i] + C.dt * l[i]; }
+            g = scp_ell_grav(o4, ts);
+            scp_ell_f(o4, g, ts, af, ty, fr, k, l);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { s[i] = s[i] + C.dt6 * (as[i] + k[i]); y[i] = y[i] + C.dt6 * (ay[i] + l[i]); }
+            th = th + C.dt6 * (((o1.w + 2.0 * o2.w) + 2.0 * o3.w) + o4.w);
+        }
+        const double v = j < 6 ? sr[j] : ar[j - 6];
+        double *out = j < 6 ? Ak + (size_t)(6 * j) * ld : Bk + (size_t)(6 * (j - 6)) * ld;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (j == 0) { cacc[i] = s[i]; F[i] = s[i]; }
+            out[(size_t)i * ld] = y[i];
+            cacc[i] = cacc[i] - y[i] * v;
+        }
+        if (imp && j >= 3) {
+            double *outb = Bk + (size_t)(6 * (j - 3)) * ld;
+            const double vb = ar[j - 3];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                outb[(size_t)i * ld] = y[i];
+                cacc[i] = cacc[i] - y[i] * vb;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ck[(size_t)i * ld] = cacc[i];
+}
+
+// true anomaly at the start of every stage, theta_tab [N][ld] (oracle/scp_ocp.py theta_table): the orbit's own clock, once per solve
+__global__ void k_scp_theta(int64_t batch, int N, size_t ld, double dt, double hdt, double dt6, int substeps,
+                            const double *__restrict__ ecc, const double *__restrict__ theta0, double *__restrict__ tab)
+{
+    const int64_t p_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p_ >= batch) return;
+    const double e = ecc[p_];
+    const double p = 1.0 - e * e;
+    const double h = sqrt(p);
+    double th = theta0[p_];
+    for (int k = 0; k < N; ++k) {
+        tab[(size_t)k * ld + p_] = th;
+        for (int ss = 0; ss < substeps; ++ss) {
+            const double w1 = scp_ell_coef(th, e, p, h, 1.0).w;
+            const double w2 = scp_ell_coef(th + hdt * w1, e, p, h, 1.0).w;
+            const double w3 = scp_ell_coef(th + hdt * w2, e, p, h, 1.0).w;
+            const double w4 = scp_ell_coef(th + dt * w3, e, p, h, 1.0).w;
+            th = th + dt6 * (((w1 + 2.0 * w2) + 2.0 * w3) + w4);
+        }
+    }
+}
+
 // passes >= 2: every stage of every still-moving problem about its reference trajectory xref [n][ld]; blockIdx.y = stage
 __global__ void __launch_bounds__(128) k_scp_linearise(ScpConst C, int64_t batch, int N, size_t ld,
                                                        const int *__restrict__ active, const double *__restrict__ xref,
-                                                       double *__restrict__ A, double *__restrict__ B, double *__restrict__ c)
+                                                       double *__restrict__ A, double *__restrict__ B, double *__restrict__ c,
+                                                       const double *__restrict__ ecc, const double *__restrict__ theta_tab)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch || (active && !active[p])) return;
@@ -147,14 +298,19 @@ __global__ void __launch_bounds__(128) k_scp_linearise(ScpConst C, int64_t batch
     for (int i = 0; i < 6; ++i) sr[i] = xref[(size_t)(9 * k + i) * ld + p];
 #pragma unroll
     for (int i = 0; i < 3; ++i) ar[i] = xref[(size_t)(9 * k + 6 + i) * ld + p];
-    scp_linearise_stage(C, sr, ar, F, A + (size_t)36 * k * ld + p, B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
+    if (C.elliptic)
+        scp_linearise_stage_ell(C, ecc[p], theta_tab[(size_t)k * ld + p], sr, ar, F, A + (size_t)36 * k * ld + p,
+                                B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
+    else
+        scp_linearise_stage(C, sr, ar, F, A + (size_t)36 * k * ld + p, B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
 }
 
 // pass 1: the reference is the nonlinear trajectory from s0 under the controls of xref (zero: free drift), linearised
 // on the way (oracle/scp_ocp.py shoot); one thread per problem, the stages follow each other
 __global__ void __launch_bounds__(128) k_scp_shoot(ScpConst C, int64_t batch, int N, size_t ld, const double *__restrict__ s0,
                                                    double *__restrict__ xref, double *__restrict__ A, double *__restrict__ B,
-                                                   double *__restrict__ c)
+                                                   double *__restrict__ c, const double *__restrict__ ecc,
+                                                   const double *__restrict__ theta_tab)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
@@ -166,7 +322,11 @@ __global__ void __launch_bounds__(128) k_scp_shoot(ScpConst C, int64_t batch, in
         for (int i = 0; i < 6; ++i) xref[(size_t)(9 * k + i) * ld + p] = sr[i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) ar[i] = xref[(size_t)(9 * k + 6 + i) * ld + p];
-        scp_linearise_stage(C, sr, ar, F, A + (size_t)36 * k * ld + p, B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
+        if (C.elliptic)
+            scp_linearise_stage_ell(C, ecc[p], theta_tab[(size_t)k * ld + p], sr, ar, F, A + (size_t)36 * k * ld + p,
+                                    B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
+        else
+            scp_linearise_stage(C, sr, ar, F, A + (size_t)36 * k * ld + p, B + (size_t)18 * k * ld + p, c + (size_t)6 * k * ld + p, ld);
 #pragma unroll
         for (int i = 0; i < 6; ++i) sr[i] = F[i];
     }

@@ -218,7 +218,8 @@ int admmb_k_scp_linearise(admmb_handle h, int32_t N, int64_t batch, const admmb_
 {
     if (!h || N < 1 || batch < 1 || !sc || !xref || !A || !B || !c || (shoot && !s0)) return ADMMB_E_BADARG;
     std::lock_guard<std::mutex> lk(h->mu);
-    if (sc->model != ADMMB_SCP_NL_CIRCULAR || !(sc->T > 0.0) || !(sc->R0 > 0.0) || sc->substeps < 0)
+    if ((sc->model != ADMMB_SCP_NL_CIRCULAR && sc->model != ADMMB_SCP_NL_ELLIPTIC) || !(sc->T > 0.0) || !(sc->R0 > 0.0) ||
+        sc->substeps < 0 || (sc->model == ADMMB_SCP_NL_ELLIPTIC && (!sc->e || !sc->theta0)))
         return fail(h, ADMMB_E_BADARG, "admmb_k_scp_linearise: bad scp parameters");
     return guarded(h, [&]() {
         UnitCtx U(h);
@@ -237,9 +238,17 @@ int admmb_k_scp_linearise(admmb_handle h, int32_t N, int64_t batch, const admmb_
         C.n2 = nmm * nmm; C.tn = 2.0 * nmm;
         C.dt = sc->T / (double)C.substeps; C.hdt = 0.5 * C.dt; C.dt6 = C.dt / 6.0;
         C.impulsive = sc->control == ADMMB_SCP_CTRL_IMPULSIVE;
+        C.elliptic = sc->model == ADMMB_SCP_NL_ELLIPTIC;
         const unsigned gb = (unsigned)((batch + 127) / 128);
-        if (shoot) k_scp_shoot<<<gb, 128, 0, U.s.stream>>>(C, batch, N, ld, ds0.p, dx.p, dA.p, dB.p, dc.p);
-        else k_scp_linearise<<<dim3(gb, (unsigned)N), 128, 0, U.s.stream>>>(C, batch, N, ld, nullptr, dx.p, dA.p, dB.p, dc.p);
+        DevBuf<double> de, dth0, dtab;
+        if (C.elliptic) {
+            U.up(de, sc->e, (size_t)batch);
+            U.up(dth0, sc->theta0, (size_t)batch);
+            dtab.alloc((size_t)N * ld);
+            k_scp_theta<<<gb, 128, 0, U.s.stream>>>(batch, N, ld, C.dt, C.hdt, C.dt6, C.substeps, de.p, dth0.p, dtab.p);
+        }
+        if (shoot) k_scp_shoot<<<gb, 128, 0, U.s.stream>>>(C, batch, N, ld, ds0.p, dx.p, dA.p, dB.p, dc.p, de.p, dtab.p);
+        else k_scp_linearise<<<dim3(gb, (unsigned)N), 128, 0, U.s.stream>>>(C, batch, N, ld, nullptr, dx.p, dA.p, dB.p, dc.p, de.p, dtab.p);
         CK(cudaGetLastError());
         U.down_rows(dA.p, stg, A, batch, 36 * N, ld);
         U.down_rows(dB.p, stg, B, batch, 18 * N, ld);

@@ -8,7 +8,7 @@ function [x, z, u, hist] = admm_scp_solve(prob, opts, scp)
 %   prob.N, prob.s0 [6 x Bsz], prob.block_type int32 [3N+2], prob.block_par [8 x (3N+2) x Bp];
 %   optional prob.q [n x Bq], per-problem prob.Q [6 x 6 x (N+1) x Bsz], prob.R [3 x 3 x N x Bsz]   (no A, B, c)
 %   opts: as admm_solve; adapt_rho and history must be off, xupdate 'auto' or 'riccati', precision 'fp64'
-%   scp : model ('nl_circular'), T, R0, nmm (default 1), substeps (default 8), max_pass, tol_abs, tol_rel,
+%   scp : model ('nl_circular' | 'nl_elliptic': chief on a Kepler orbit, then scp.e, scp.theta0 [Bsz], R0 = semi-major axis), T, R0, nmm (default 1), substeps (default 8), max_pass, tol_abs, tol_rel,
 %         control ('zoh' (default): thrust acceleration held over a stage | 'impulsive': velocity increment, then a coast)
 %
 %   hist: the fields of admm_solve for every problem's LAST convex solve, plus

@@ -163,8 +163,15 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     admmb_scp sc;
     std::memset(&sc, 0, sizeof(sc));
     if (S) {
-        static const char *const models[] = {"", "nl_circular"};
-        sc.model = opt_enum(S, "model", models, 2, ADMMB_SCP_NL_CIRCULAR);
+        static const char *const models[] = {"", "nl_circular", "nl_elliptic"};
+        sc.model = opt_enum(S, "model", models, 3, ADMMB_SCP_NL_CIRCULAR);
+        const mxArray *se = mxGetField(S, 0, "e"), *sth = mxGetField(S, 0, "theta0");
+        if (sc.model == ADMMB_SCP_NL_ELLIPTIC) {
+            if (!se || !sth || mxGetNumberOfElements(se) != Bsz || mxGetNumberOfElements(sth) != Bsz)
+                mexErrMsgIdAndTxt("admm:ADMMB_E_BADARG", "scp.e and scp.theta0 must have one entry per problem");
+            sc.e = dptr(se, "scp.e");
+            sc.theta0 = dptr(sth, "scp.theta0");
+        }
         sc.substeps = (int32_t)opt_scalar(S, "substeps", 0);
         sc.T = opt_scalar(S, "T", 0.0);
         sc.nmm = opt_scalar(S, "nmm", 0.0);

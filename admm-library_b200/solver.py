@@ -53,17 +53,21 @@ def make_generator(gen: dict):
     return g, (e, th)
 
 
-SCP_MODEL = {"nl_circular": 1}   # include/admm_b200.h ADMMB_SCP_*
+SCP_MODEL = {"nl_circular": 1, "nl_elliptic": 2}   # include/admm_b200.h ADMMB_SCP_*
 SCP_CONTROL = {"zoh": 0, "impulsive": 1}   # ADMMB_SCP_CTRL_*
 
 
 def make_scp(scp: dict) -> L.Scp:
     """scp = dict(T=..., R0=..., max_pass=..., tol_abs=..., tol_rel=..., model="nl_circular", nmm=1.0, substeps=8,
-    control="zoh" | "impulsive")."""
-    return L.Scp(model=SCP_MODEL[scp.get("model", "nl_circular")], substeps=int(scp.get("substeps", 0)),
-                 T=float(scp["T"]), nmm=float(scp.get("nmm", 0.0)), R0=float(scp["R0"]), max_pass=int(scp["max_pass"]),
-                 tol_abs=float(scp.get("tol_abs", 0.0)), tol_rel=float(scp.get("tol_rel", 0.0)),
-                 control=SCP_CONTROL[scp.get("control", "zoh")])
+    control="zoh" | "impulsive"; model="nl_elliptic" adds e=[batch], theta0=[batch])."""
+    e = None if scp.get("e") is None else np.ascontiguousarray(scp["e"], dtype=np.float64)
+    th = None if scp.get("theta0") is None else np.ascontiguousarray(scp["theta0"], dtype=np.float64)
+    sc = L.Scp(model=SCP_MODEL[scp.get("model", "nl_circular")], substeps=int(scp.get("substeps", 0)),
+               T=float(scp["T"]), nmm=float(scp.get("nmm", 0.0)), R0=float(scp["R0"]), max_pass=int(scp["max_pass"]),
+               tol_abs=float(scp.get("tol_abs", 0.0)), tol_rel=float(scp.get("tol_rel", 0.0)),
+               control=SCP_CONTROL[scp.get("control", "zoh")], e=_dp(e), theta0=_dp(th))
+    sc._keep = (e, th)        # the struct holds raw pointers into these
+    return sc
 
 
 def _dp(a):

@@ -203,8 +203,11 @@ int admmb_solve_generated(admmb_handle h, const admmb_problem *prob, const admmb
  * table and (optionally) q / per-problem Q, R are uploaded; prob->A, B, c, dyn_batched are ignored.
  * Oracle: oracle/scp_ocp.py (same IEEE operations in the same order; every pass is bit-identical). */
 enum {
-    ADMMB_SCP_NL_CIRCULAR = 1    /* deputy about a chief on a circular orbit of radius R0: LVLH frame, full two-body
+    ADMMB_SCP_NL_CIRCULAR = 1,   /* deputy about a chief on a circular orbit of radius R0: LVLH frame, full two-body
                                     gravity, zero-order-hold thrust acceleration (linearised at r = 0: Clohessy-Wiltshire) */
+    ADMMB_SCP_NL_ELLIPTIC = 2    /* chief on a Kepler orbit of eccentricity e[p] from true anomaly theta0[p]; R0 is the
+                                    semi-major axis, the time unit 1 / mean motion (nmm must be 0 or 1); linearised at
+                                    r = 0: the model of ADMMB_GEN_ELLIPTIC_ZOH (config 4)                               */
 };
 enum {
     ADMMB_SCP_CTRL_ZOH = 0,       /* thrust acceleration held over the stage (low-thrust transfers, configs 3 / 4)   */
@@ -219,6 +222,8 @@ typedef struct admmb_scp {
     int32_t max_pass;            /* linearise + solve passes at most (>= 1)                      */
     double tol_abs, tol_rel;     /* per-problem stop: max|x - x_ref| <= tol_abs + tol_rel max|x|, last solve converged */
     int32_t control;             /* ADMMB_SCP_CTRL_*: how the three controls of a stage act                          */
+    const double *e;             /* NL_ELLIPTIC: [batch] eccentricities, 0 <= e < 1                                   */
+    const double *theta0;        /* NL_ELLIPTIC: [batch] true anomaly at the start of stage 0                         */
 } admmb_scp;
 /* per-problem SCP outputs; caller-allocated, any pointer may be NULL */
 typedef struct admmb_scp_result {

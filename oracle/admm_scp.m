@@ -15,11 +15,14 @@ function [x, z, u, hist] = admm_scp(prob, opts, scp)
 %          mu = n^2 R0^3, full two-body gravity, zero-order-hold thrust acceleration a:
 %            rho = [R0 + x; y; z],  g = n^2 - mu/|rho|^3,  k = mu/|rho|^3
 %            x'' =  2 n y' + g (R0 + x) + a_x ,   y'' = -2 n x' + g y + a_y ,   z'' = -k z + a_z
+%          (the elliptic-chief model 'nl_elliptic' of the library is stated in oracle/scp_ocp.py only: this text covers
+%          'nl_circular' with both control models)
 %   pass : A_k = dF/ds, B_k = dF/da, c_k = F(s_k, a_k) - A_k s_k - B_k a_k about the reference (RK4 of the state and
 %          its variational equations); convex subproblem by admm_ocp, warm-started from the previous pass;
 %          a problem leaves the loop when max|x - x_ref| <= tol_abs + tol_rel max|x|.
 %          First reference: free drift from s0.
 
+    if isfield(scp,'model') && ~strcmp(scp.model,'nl_circular'), error('admm_scp: only the nl_circular model is written out here'); end
     N = prob.N;  n = 9*N + 6;  Bsz = size(prob.s0, 2);
     if ~isfield(scp,'nmm') || scp.nmm == 0, scp.nmm = 1; end
     if ~isfield(scp,'substeps') || scp.substeps == 0, scp.substeps = 8; end

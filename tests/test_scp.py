@@ -108,12 +108,44 @@ def test_scp_controls_reach_the_target_in_the_nonlinear_dynamics(P, cpu_oracle):
 
 
 def _fixture_workload(P, g):
-    make = P.scp_nonlinear_impulsive if str(g["control"]) == "impulsive" else P.scp_nonlinear_rendezvous
+    make = (P.scp_nonlinear_impulsive if str(g["control"]) == "impulsive" else
+            P.scp_nonlinear_elliptic if str(g["model"]) == "nl_elliptic" else P.scp_nonlinear_rendezvous)
     return make(int(g["batch"]), int(g["N"]), seed=int(g["seed"]), scale=float(g["scale"]), substeps=int(g["substeps"]))
 
 
+def test_elliptic_model_limits(P):
+    """model = "nl_elliptic": (i) close to the chief the stage records are the linear elliptic STMs of the generator
+    oracle (config 4's model, itself checked against solve_ivp in tests/test_oracle.py); (ii) with e = 0 it is the
+    circular model; (iii) the true-anomaly table advances by the orbit's own clock (Kepler's equation)."""
+    from oracle import gen_ocp
+    rng = np.random.Generator(np.random.PCG64(1))
+    B, N = 4, 6
+    e, th0, T = rng.uniform(0.05, 0.5, B), rng.uniform(0.0, 6.0, B), 2.0 * np.pi / N
+    scp = dict(model="nl_elliptic", T=T, R0=7000.0, substeps=8, e=e, theta0=th0)
+    Ag, Bg = gen_ocp.elliptic_stage_matrices(e, th0, N, T, 8)
+    A, Bm, c = scp_ocp.linearise(np.full((B, 9 * N + 6), 1e-7), N, scp)
+    assert np.abs(A - Ag).max() <= 1e-7 and np.abs(Bm - Bg).max() <= 1e-7 and np.abs(c).max() <= 1e-12
+    xr = 30.0 * rng.standard_normal((B, 9 * N + 6))
+    A0, B0, c0 = scp_ocp.linearise(xr, N, dict(scp, e=np.zeros(B)))
+    Ac, Bc, cc = scp_ocp.linearise(xr, N, dict(model="nl_circular", T=T, R0=7000.0, substeps=8))
+    assert np.abs(A0 - Ac).max() <= 1e-13 and np.abs(B0 - Bc).max() <= 1e-13 and np.abs(c0 - cc).max() <= 1e-11
+    # one full period brings the true anomaly back (mod 2 pi): N stages of 2 pi / N at mean motion 1
+    tab = scp_ocp.theta_table(e, th0, N + 1, T, 64)
+    assert np.abs((tab[:, N] - th0) - 2.0 * np.pi).max() <= 1e-7
+
+
+def test_scp_elliptic_controls_reach_the_target(P):
+    B, N = 4, 14
+    prob, scp, opts = P.scp_nonlinear_elliptic(B, N, seed=3, scale=30.0)
+    x, z, u, info = scp_ocp.scp_solve(prob, scp, opts)
+    assert (info["scp_status"] == 0).all() and (info["status"] == 0).all() and info["passes"].min() >= 3
+    ctrl = z[:, :9 * N].reshape(B, N, 9)[:, :, 6:9]
+    miss = np.abs(scp_ocp.propagate_nonlinear(prob["s0"], ctrl, N, scp)).max(axis=1)
+    assert miss.max() <= 5e-3
+
+
 def test_scp_golden_fixtures_exist():
-    assert len(SCP_GOLDEN) >= 3
+    assert len(SCP_GOLDEN) >= 4
 
 
 def test_impulsive_stage_is_a_coast_after_the_velocity_increment():
@@ -227,6 +259,26 @@ def test_scp_impulsive_linearise_and_solve_bit_identical(solver, P):
     assert np.array_equal(Bm, A[:, :, :, 3:6])
     prob, scp, opts = P.scp_nonlinear_impulsive(B, 12, seed=9, scale=30.0, substeps=3)
     _assert_scp_equal(solver.scp_solve(prob, scp, opts), scp_ocp.scp_solve(prob, scp, opts))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("control", ["zoh", "impulsive"])
+def test_scp_elliptic_linearise_and_solve_bit_identical(solver, P, control):
+    rng = np.random.Generator(np.random.PCG64(78))
+    B, N = 41, 7
+    scp = dict(model="nl_elliptic", control=control, T=2.0 * np.pi / N, R0=6900.0, substeps=3,
+               e=rng.uniform(0.0, 0.7, B), theta0=rng.uniform(-5.0, 5.0, B))
+    xref = 40.0 * rng.standard_normal((B, 9 * N + 6))
+    A, Bm, c, _ = solver.k_scp_linearise(N, scp, xref)
+    Ao, Bo, co = scp_ocp.linearise(xref, N, scp)
+    assert np.array_equal(A, Ao) and np.array_equal(Bm, Bo) and np.array_equal(c, co)
+    s0 = 30.0 * rng.standard_normal((B, 6))
+    A, Bm, c, xr = solver.k_scp_linearise(N, scp, np.zeros((B, 9 * N + 6)), s0=s0)
+    xo, Ao, Bo, co = scp_ocp.shoot(s0, None, N, scp)
+    assert np.array_equal(xr, xo) and np.array_equal(A, Ao) and np.array_equal(Bm, Bo) and np.array_equal(c, co)
+    if control == "zoh":
+        prob, scp, opts = P.scp_nonlinear_elliptic(B, 12, seed=33, scale=25.0, substeps=3)
+        _assert_scp_equal(solver.scp_solve(prob, scp, opts), scp_ocp.scp_solve(prob, scp, opts))
 
 
 @pytest.mark.gpu
