@@ -32,7 +32,7 @@ int iterate_wg_tile_width(const IterLaunchCtx &c)
     if (!c.fast_pattern || !c.decoupled || c.has_c || c.has_q || c.par_batched || c.rows_zu <= 0) return 0;
     static const int tw_cap = getenv("ADMMB_WG_TW") ? atoi(getenv("ADMMB_WG_TW")) : 32;      // developer knob
     for (int tw = tw_cap < 32 ? tw_cap : 32; tw >= WG_MIN_TW; --tw)
-        if (wg_layout(c.N, c.rows_zu, tw).total <= WG_SMEM_MAX) return tw;
+        if (wg_layout(c.N, c.rows_zu, tw, c.time_invariant ? D_AIN : FD).total <= WG_SMEM_MAX) return tw;
     return 0;
 }
 
@@ -41,7 +41,7 @@ bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt)
 {
     const int tw = iterate_wg_tile_width(c);
     if (tw == 0) return false;
-    const size_t smem = wg_layout(c.N, c.rows_zu, tw).total;
+    const size_t smem = wg_layout(c.N, c.rows_zu, tw, c.time_invariant ? D_AIN : FD).total;
     const int ntiles = (P.n_active + tw - 1) / tw;
     const int grid = ntiles < c.num_sms ? ntiles : c.num_sms;
 #define WG_LAUNCH(A, T)                                                                   \

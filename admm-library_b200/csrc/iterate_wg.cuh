@@ -45,7 +45,10 @@ struct WgLayout {                                // byte offsets inside the dyna
 // Tile arrays are stored PROBLEM-major: the rows of one problem are contiguous, lane p starts at p * pitch.  A row is
 // then a compile-time offset from a per-lane pointer (no index arithmetic on the sequential chains), and an odd pitch
 // keeps a warp's 64-bit accesses conflict-free (16 lanes of a half-warp hit 16 distinct bank pairs).
-__host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW)
+// fw = doubles per stage of the factor copy in shared memory: the whole packed record (FD), or -- time-invariant dynamics,
+// whose A_k, B_k live in the chain warps' registers -- only K, Acl, Hinv, E (the first D_AIN = 46 doubles): 18 KB instead of
+// 35 KB at N = 50, 37 KB instead of 70 KB at N = 100, i.e. tiles of 32 instead of 30 and of 15 instead of 12 problems.
+__host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW, int fw = FD)
 {
     WgLayout L;
     L.TW = TW;
@@ -57,7 +60,7 @@ __host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW)
     L.bars = o; o += 8 * (size_t)(N + 1);        // bC2[0..N]: a_k / s_N published by both chain warps
     o = (o + 15) / 16 * 16;
     L.prog = o; o += 16;                         // blocks finished by each prox warp since the launch began (4 x u32)
-    L.fac = o; o += sizeof(double) * FD * (size_t)N;
+    L.fac = o; o += sizeof(double) * (size_t)fw * (size_t)N;
     L.par = o; o += sizeof(double) * 8 * (size_t)nsb;          // parameter table, compact: one record per split block
     L.typ = o; o += sizeof(int) * (size_t)((nsb + 3) / 4 * 4);
     const size_t col = sizeof(double) * (size_t)TW;
@@ -166,7 +169,8 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
 {
     extern __shared__ __align__(16) unsigned char wg_smem[];
     const int N = P.N;
-    const WgLayout L = wg_layout(N, P.rows_zu, TW);
+    constexpr int FW = TI ? D_AIN : FD;                  // stage pitch of the factor copy in shared memory (see wg_layout)
+    const WgLayout L = wg_layout(N, P.rows_zu, TW, FW);
     const int tid = threadIdx.x, warp = tid >> 5;
     // lanes beyond the tile width are exact clones of the tile's last lane (same problem, same state, same values
     // written to the same addresses), so no access has to be predicated on the lane
@@ -193,8 +197,13 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
         mbar_init(mbar, 1);
         for (int k = 0; k <= N; ++k) mbar_init(bC2 + 8u * k, 2);      // both chain warps
         for (int w = 0; w < WG_PROX; ++w) asm volatile("st.shared.u32 [%0], %1;" ::"r"(prog_s + 4u * w), "r"(0) : "memory");
-        mbar_expect_tx(mbar, (uint32_t)(FD * N * 8));
-        bulk_g2s(fac_s, P.fac_dec, (uint32_t)(FD * N * 8), mbar);
+        mbar_expect_tx(mbar, (uint32_t)(FW * N * 8));
+        if (TI) {   // K, Acl, Hinv, E of every stage: N copies of 368 bytes (both ends 16-byte aligned: 704 k and 368 k)
+            for (int k = 0; k < N; ++k)
+                bulk_g2s(fac_s + (uint32_t)(k * FW) * 8u, P.fac_dec + (size_t)k * FD, (uint32_t)(FW * 8), mbar);
+        } else {
+            bulk_g2s(fac_s, P.fac_dec, (uint32_t)(FD * N * 8), mbar);
+        }
     }
     {
         double *parS = reinterpret_cast<double *>(wg_smem + L.par);
@@ -214,17 +223,19 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     mbar_wait(mbar, 0);
 
     double Ai[4][4], Bi[4][2], Ac[2][2], Bc[2];          // TI: the stage-invariant dynamics of this warp's chain
-    if (TI && chain_in) {
+    if (TI && chain_in) {                                // from the global record of stage 0 (not part of the compact copy)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            wg_ld4(fac_s + (D_AIN + 4 * r) * 8, Ai[r]);
-            wg_ld2(fac_s + (D_BIN + 2 * r) * 8, Bi[r][0], Bi[r][1]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Ai[r][c] = __ldg(P.fac_dec + D_AIN + 4 * r + c);
+            Bi[r][0] = __ldg(P.fac_dec + D_BIN + 2 * r);
+            Bi[r][1] = __ldg(P.fac_dec + D_BIN + 2 * r + 1);
         }
     }
     if (TI && chain_c) {
-        wg_ld2(fac_s + D_AC * 8, Ac[0][0], Ac[0][1]);
-        wg_ld2(fac_s + (D_AC + 2) * 8, Ac[1][0], Ac[1][1]);
-        wg_ld2(fac_s + D_BC * 8, Bc[0], Bc[1]);
+        Ac[0][0] = __ldg(P.fac_dec + D_AC); Ac[0][1] = __ldg(P.fac_dec + D_AC + 1);
+        Ac[1][0] = __ldg(P.fac_dec + D_AC + 2); Ac[1][1] = __ldg(P.fac_dec + D_AC + 3);
+        Bc[0] = __ldg(P.fac_dec + D_BC); Bc[1] = __ldg(P.fac_dec + D_BC + 1);
     }
 
     const size_t ld = P.ld;
@@ -296,7 +307,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     struct In { double z[2], u[2], h0[2], h1[2], e0[4], e1[4], k0[4], k1[4], ac[4][4]; };
                     wg_stage_loop<In>(N - 1, -1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u;
+                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
                             wg_ld4(fk + D_KIN * 8, in.k0);
                             wg_ld4(fk + (D_KIN + 4) * 8, in.k1);
 #pragma unroll
@@ -345,7 +356,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     struct In { double d[2], kn[2][4], an[4][4], bn[4][2]; };
                     wg_stage_loop<In>(0, 1, N,
                         [&](int k, In &o) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u, dk = ds + (uint32_t)(3 * k) * 8u;
+                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u, dk = ds + (uint32_t)(3 * k) * 8u;
                             wg_ld4(fk + D_KIN * 8, o.kn[0]);
                             wg_ld4(fk + (D_KIN + 4) * 8, o.kn[1]);
                             if (!TI) {
@@ -405,7 +416,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     struct In { double z, u, hc[2], ec[2], kc[2], a0[2], a1[2]; };
                     wg_stage_loop<In>(N - 1, -1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u;
+                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
                             wg_ld2(fk + D_KC * 8, in.kc[0], in.kc[1]);
                             wg_ld2(fk + D_ACLC * 8, in.a0[0], in.a0[1]);
                             wg_ld2(fk + (D_ACLC + 2) * 8, in.a1[0], in.a1[1]);
@@ -434,7 +445,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     struct In { double kc[2], a0[2], a1[2], bc[2], d2; };
                     wg_stage_loop<In>(0, 1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FD) * 8u;
+                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
                             wg_ld2(fk + D_KC * 8, in.kc[0], in.kc[1]);
                             if (!TI) {
                                 wg_ld2(fk + D_AC * 8, in.a0[0], in.a0[1]);
