@@ -399,7 +399,7 @@ def main():
         roofline["kernel"] = "k_dense_xupdate_tf32 + k_prox_cond_tf32 (pair, one graph node each per iteration)"
         roofline["traffic"] = None
     else:
-        roofline["kernel"] = ("k_admm_iterate2 / k_admm_iterate while more than 12,288 problems run (streams z, u, d through HBM), "
+        roofline["kernel"] = ("k_admm_iterate2 / k_admm_iterate while more than 14,208 problems run (three 32-problem tiles per SM) (streams z, u, d through HBM), "
                               "k_admm_iterate_wg below (iterates resident in shared memory: no HBM bytes per iteration, "
                               "bound by the length of the sweep recurrences -- DESIGN 4.3)")
 
@@ -497,10 +497,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_configs and name == "target65k" and args.precision == "f64" \
             and args.xupdate == "auto" and not args.batch:
         configs = {}
-        kernels = {"cfg2": "k_admm_iterate_wg (4,096 <= 12,288 running problems from the start)",
-                   "cfg3": "k_admm_iterate_wg (N = 100: 12 problems per resident tile)",
+        kernels = {"cfg2": "k_admm_iterate_wg (4,096 <= 14,208 running problems from the start)",
+                   "cfg3": "k_admm_iterate_wg (N = 100: 15 problems per resident tile)",
                    "cfg4": "k_admm_iterate_pptma (per-problem stage records streamed by TMA)",
-                   "cfg5": "k_admm_iterate2 / k_admm_iterate, k_admm_iterate_wg below 12,288 running problems (adaptive rho)"}
+                   "cfg5": "k_admm_iterate2 / k_admm_iterate, k_admm_iterate_wg below 14,208 running problems (adaptive rho)"}
         t_cfg0 = time.perf_counter()
         for cname in ("cfg2", "cfg3", "cfg4", "cfg5"):
             if time.perf_counter() - t_cfg0 > 75.0:
