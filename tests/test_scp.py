@@ -348,11 +348,13 @@ def test_scp_max_pass_and_quadratic_cost(solver, P):
 
 
 @pytest.mark.gpu
-def test_scp_two_gpus_same_bits(pkg, P, solver):
+@pytest.mark.parametrize("workload", ["circular", "elliptic"])
+def test_scp_two_gpus_same_bits(pkg, P, solver, workload):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    prob, scp, opts = P.scp_nonlinear_rendezvous(70, 10, seed=77, scale=30.0, substeps=3)
+    make = P.scp_nonlinear_elliptic if workload == "elliptic" else P.scp_nonlinear_rendezvous     # per-problem e, theta0 are sharded too
+    prob, scp, opts = make(70, 10, seed=77, scale=30.0, substeps=3)
     one = solver.scp_solve(prob, scp, opts)
     with pkg.Solver(devices=[0, 1]) as s2:
         two = s2.scp_solve(prob, scp, opts)
