@@ -387,6 +387,15 @@ static bool wg_takes(int64_t n_active, int tile, int num_sms)
     return (tiles + num_sms - 1) / num_sms <= 3;
 }
 
+// per-problem models: widest working set the streamed-record warp-group kernel takes when the choice is the library's, in
+// passes (tiles per CTA), measured against k_admm_iterate_pptma (scripts/variant_rates.py cfg4); ADMMB_WGPP_PASSES overrides
+static bool wgpp_takes(int64_t n_active, int tile, int num_sms)
+{
+    static const int64_t max_passes = getenv("ADMMB_WGPP_PASSES") ? atoll(getenv("ADMMB_WGPP_PASSES")) : 2;
+    const int64_t tiles = (n_active + tile - 1) / tile;
+    return (tiles + num_sms - 1) / num_sms <= max_passes;
+}
+
 template <bool FSH, bool FSMEM>
 void Shard::launch_iterate(const IterParams &P, bool adapt)
 {
@@ -403,7 +412,14 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
         else launch_iterate_smem(c, P, adapt);
     }
     else if (FSH) launch_iterate_gshared(c, P, adapt);
-    else if (!launch_iterate_pptma(c, P, adapt)) launch_iterate_pp(c, P, adapt);
+    else {
+        // per-problem models: the warp-group kernel with streamed records when pinned, or -- the library's choice -- on narrow
+        // working sets, where one problem per thread is bound by a lone warp's instruction stream (52-70 us per iteration)
+        const int tw = iterate_wgpp_tile_width(c, adapt && P.has_P);
+        const bool wgpp = tw > 0 && (kernel_variant == KV_WG || (kernel_variant == KV_AUTO && wgpp_takes(P.n_active, tw, num_sms)));
+        if (wgpp && launch_iterate_wgpp(c, P, adapt)) last_kernel = KV_WG;
+        else if (!launch_iterate_pptma(c, P, adapt)) launch_iterate_pp(c, P, adapt);
+    }
     ++launches;
 }
 
@@ -816,6 +832,7 @@ void Shard::run(const admmb_opts *op, admmb_result *res)
             IterLaunchCtx c{stream, num_sms, N, nb, par_batched, has_c, has_q, fast_pattern, decoupled, false, kernel_variant,
                             rows_zu, device, time_invariant, nullptr};
             if (shared_factor && fsmem) wg_tile = kernel_variant == KV_PINT && pint_ready ? iterate_pint_tile_width(c) : iterate_wg_tile_width(c);
+            else if (!shared_factor) wg_tile = iterate_wgpp_tile_width(c, adapt && has_P);
         }
         int done_iters = 0;
         while (width > 0 && done_iters < op->max_iter && !(tf32_tail && width <= tail_width)) {

@@ -27,6 +27,10 @@ bool iterate_res_eligible(const IterLaunchCtx &c);
 // shared factor, the fast block pattern, no affine term / linear cost / per-problem parameters)
 bool launch_iterate_wg(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 int iterate_wg_tile_width(const IterLaunchCtx &c);
+// the same kernel for per-problem decoupled models: stage records streamed through a TMA ring; refactors: a rho change would
+// need a new factor inside the kernel (adaptive rho with a quadratic cost), which this form does not do
+bool launch_iterate_wgpp(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+int iterate_wgpp_tile_width(const IterLaunchCtx &c, bool refactors);
 // parallel-in-time kernel (iterate_pint.cuh): eight warps sweep eight chunks of stages at the same time;
 // same eligibility as the warp-group kernel; FP64 but not the oracle's operation order, hence opt-in (KV_PINT) only
 bool launch_iterate_pint(const IterLaunchCtx &c, const IterParams &P, bool adapt);

@@ -28,18 +28,27 @@
 #ifdef WG_TIMING
 #include <cstdio>
 #endif
+#include <cuda.h>
 #include "kernels.cuh"
 
 namespace admmb {
 
 constexpr int WG_WARPS = 8;
+// PP (per-problem models, config 4): the stage records of the tile's problems are streamed through a ring of WG_PP_R
+// shared-memory slots by TMA (one box of [record rows] x [TW columns] per sweep stage, issued by warp 4, which is
+// otherwise idle) instead of being read from a shared factor table; full / empty mbarriers per slot.
+constexpr int WG_PP_R = 8;                       // ring slots (power of two)
+constexpr int WG_PP_ROWS = D_AIN;                // rows of a slot: a backward stage needs record rows 0..45, a forward stage 10 + 30
+struct WgPpMaps {
+    CUtensorMap mB, mF0, mF1;                    // boxes of 46 / 10 / 30 rows x TW columns over fac_dec [FD*N][ld]
+};
 constexpr int WG_MIN_TW = 8;                     // narrower tiles waste more than 3/4 of every warp: not worth it
 constexpr int WG_PROX = 4;                       // prox warps
 
 struct WgLayout {                                // byte offsets inside the dynamic shared memory of one CTA
     int TW;                                      // tile width: problems per CTA
     int rz, rd, rg;                              // doubles per problem in the z / u, d and g arrays (odd: see below)
-    size_t bars, prog, fac, par, typ, z, u, d, g, s0, nrm, total;
+    size_t bars, prog, fac, par, typ, z, u, d, g, s0, nrm, rbar, ring, total;
 };
 
 // Tile arrays are stored PROBLEM-major: the rows of one problem are contiguous, lane p starts at p * pitch.  A row is
@@ -48,7 +57,7 @@ struct WgLayout {                                // byte offsets inside the dyna
 // fw = doubles per stage of the factor copy in shared memory: the whole packed record (FD), or -- time-invariant dynamics,
 // whose A_k, B_k live in the chain warps' registers -- only K, Acl, Hinv, E (the first D_AIN = 46 doubles): 18 KB instead of
 // 35 KB at N = 50, 37 KB instead of 70 KB at N = 100, i.e. tiles of 32 instead of 30 and of 15 instead of 12 problems.
-__host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW, int fw = FD)
+__host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW, int fw = FD, bool pp = false)
 {
     WgLayout L;
     L.TW = TW;
@@ -70,6 +79,13 @@ __host__ __device__ inline WgLayout wg_layout(int N, int rows_zu, int TW, int fw
     L.g = o; o += col * L.rg;
     L.s0 = o; o += col * 7;
     L.nrm = o; o += col * 15;                    // two sets of five sums, alternating by iteration parity; five roots
+    L.rbar = L.ring = 0;
+    if (pp) {                                    // full[R], empty[R] mbarriers, then R slots of WG_PP_ROWS x TW doubles (128-byte aligned)
+        o = (o + 15) / 16 * 16;
+        L.rbar = o; o += 16 * (size_t)WG_PP_R;
+        o = (o + 127) / 128 * 128;
+        L.ring = o; o += (size_t)WG_PP_R * WG_PP_ROWS * col;
+    }
     L.total = (o + 15) / 16 * 16;
     return L;
 }
@@ -94,6 +110,33 @@ __device__ __forceinline__ void wg_ld4(uint32_t a, double (&r)[4])
 {
     wg_ld2(a, r[0], r[1]);
     wg_ld2(a + 16, r[2], r[3]);
+}
+
+// Factor entries `off .. off+3` of the current stage.  Shared table: fk = address of the stage's record, one broadcast
+// 128-bit load per pair.  PP: fk = address of this lane's column in the ring slot, one 64-bit load per entry; slot row of
+// record offset `off`: off below 46, off - 36 above (a forward slot is K (10 rows) followed by A, B (30 rows)); rp = row pitch.
+template <bool PP>
+__device__ __forceinline__ void wgf_ld2(uint32_t fk, int off, uint32_t rp, double &x, double &y)
+{
+    if (PP) {
+        const uint32_t a = fk + (uint32_t)(off < D_AIN ? off : off - 36) * rp;
+        x = wg_ld(a);
+        y = wg_ld(a + rp);
+    } else {
+        wg_ld2(fk + (uint32_t)off * 8u, x, y);
+    }
+}
+template <bool PP>
+__device__ __forceinline__ void wgf_ld4(uint32_t fk, int off, uint32_t rp, double (&r)[4])
+{
+    wgf_ld2<PP>(fk, off, rp, r[0], r[1]);
+    wgf_ld2<PP>(fk, off + 2, rp, r[2], r[3]);
+}
+
+__device__ __forceinline__ void wg_tma(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 
 // Per-stage hand-over between warps.  The producer warp has written shared memory with all its lanes; __syncwarp orders
@@ -133,7 +176,8 @@ __device__ __forceinline__ void wg_wait_spin(uint32_t bar, uint32_t parity)
 // Stage loop with the operands of the next stage loaded (into registers) BEFORE the current stage's arithmetic and
 // stores: a warp issues in order, so without this every stage would start by waiting out its own load latency.
 // Stage j = 0 .. count-1 is k = k0 + j * stride.  Branch-free body: the prefetch past the end re-reads the last stage.
-template <class In, class LoadFn, class WorkFn>
+// EXACT: every stage is loaded exactly once (a load consumes a ring slot: PP), at the price of one branch per pair of stages.
+template <class In, bool EXACT = false, class LoadFn, class WorkFn>
 __device__ __forceinline__ void wg_stage_loop(const int k0, const int stride, const int count, LoadFn load, WorkFn work)
 {
     if (count <= 0) return;
@@ -144,7 +188,8 @@ __device__ __forceinline__ void wg_stage_loop(const int k0, const int stride, co
     for (int j = 0; j + 1 < count; j += 2, k += 2 * stride) {
         load(k + stride, b);
         work(k, a);
-        load(j + 2 < count ? k + 2 * stride : klast, a);
+        if (EXACT) { if (j + 2 < count) load(k + 2 * stride, a); }
+        else load(j + 2 < count ? k + 2 * stride : klast, a);
         work(k + stride, b);
     }
     if (count & 1) work(klast, a);
@@ -163,14 +208,15 @@ __device__ long long wg_klog[3][64];               // per stage: a_k published (
 
 // TI: A_k, B_k do not depend on the stage (time-invariant dynamics, e.g. Clohessy-Wiltshire with a fixed step): the chain
 // warps keep them in registers for the whole launch instead of re-reading 30 doubles per stage on the forward sweep
-template <bool ADAPT, bool TI>
+template <bool ADAPT, bool TI, bool PP = false>
 __global__ void __launch_bounds__(WG_WARPS * 32, 1)
-k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
+k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW, const __grid_constant__ WgPpMaps maps)
 {
-    extern __shared__ __align__(16) unsigned char wg_smem[];
+    static_assert(!(TI && PP), "per-problem models are not time-invariant");
+    extern __shared__ __align__(128) unsigned char wg_smem[];
     const int N = P.N;
-    constexpr int FW = TI ? D_AIN : FD;                  // stage pitch of the factor copy in shared memory (see wg_layout)
-    const WgLayout L = wg_layout(N, P.rows_zu, TW, FW);
+    constexpr int FW = PP ? 0 : (TI ? D_AIN : FD);       // stage pitch of the factor copy in shared memory (see wg_layout)
+    const WgLayout L = wg_layout(N, P.rows_zu, TW, FW, PP);
     const int tid = threadIdx.x, warp = tid >> 5;
     // lanes beyond the tile width are exact clones of the tile's last lane (same problem, same state, same values
     // written to the same addresses), so no access has to be predicated on the lane
@@ -193,12 +239,24 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
     const int prox = warp == 2 ? 0 : warp == 3 ? 1 : warp == 6 ? 2 : warp == 7 ? 3 : -1;
 
     // ---- once per CTA: factor (one TMA bulk copy), hand-over barriers, compact parameter table and block types
+    // PP ring: full[s] at rbar + 8 s (one arrival + the TMA bytes), empty[s] at rbar + 8 (R + s) (both chain warps)
+    const uint32_t rfull = sm0 + (uint32_t)L.rbar, rempty = rfull + 8u * WG_PP_R, ring_s = sm0 + (uint32_t)L.ring;
+    const uint32_t rp = (uint32_t)TW * 8u;               // row pitch of a slot
+    const uint32_t slot_bytes = (uint32_t)WG_PP_ROWS * rp;
+    uint32_t cstep = 0, pstep = 0;                       // ring steps consumed (chain warps) / produced (warp 4) since the launch began
     if (tid == 0) {
         mbar_init(mbar, 1);
         for (int k = 0; k <= N; ++k) mbar_init(bC2 + 8u * k, 2);      // both chain warps
         for (int w = 0; w < WG_PROX; ++w) asm volatile("st.shared.u32 [%0], %1;" ::"r"(prog_s + 4u * w), "r"(0) : "memory");
+        if (PP) {
+            for (int i = 0; i < WG_PP_R; ++i) { mbar_init(rfull + 8u * i, 1); mbar_init(rempty + 8u * i, 2); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         mbar_expect_tx(mbar, (uint32_t)(FW * N * 8));
-        if (TI) {   // K, Acl, Hinv, E of every stage: N copies of 368 bytes (both ends 16-byte aligned: 704 k and 368 k)
+        if (PP) {
+            // nothing to copy: the arrival of expect_tx(0) completes the phase
+        } else if (TI) {   // K, Acl, Hinv, E of every stage: N copies of 368 bytes (both ends 16-byte aligned: 704 k and 368 k)
             for (int k = 0; k < N; ++k)
                 bulk_g2s(fac_s + (uint32_t)(k * FW) * 8u, P.fac_dec + (size_t)k * FD, (uint32_t)(FW * 8), mbar);
         } else {
@@ -305,17 +363,28 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                 }
                 {
                     struct In { double z[2], u[2], h0[2], h1[2], e0[4], e1[4], k0[4], k1[4], ac[4][4]; };
-                    wg_stage_loop<In>(N - 1, -1, N,
+                    wg_stage_loop<In, PP>(N - 1, -1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
-                            wg_ld4(fk + D_KIN * 8, in.k0);
-                            wg_ld4(fk + (D_KIN + 4) * 8, in.k1);
+                            uint32_t fk, sl = 0;
+                            if (PP) {                                   // this stage's records: wait for the TMA box
+                                sl = cstep & (WG_PP_R - 1);
+                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                            } else {
+                                fk = fac_s + (uint32_t)(k * FW) * 8u;
+                            }
+                            wgf_ld4<PP>(fk, D_KIN, rp, in.k0);
+                            wgf_ld4<PP>(fk, D_KIN + 4, rp, in.k1);
 #pragma unroll
-                            for (int l = 0; l < 4; ++l) wg_ld4(fk + (D_ACLIN + 4 * l) * 8, in.ac[l]);
-                            wg_ld2(fk + D_HIN * 8, in.h0[0], in.h0[1]);
-                            wg_ld2(fk + (D_HIN + 2) * 8, in.h1[0], in.h1[1]);
-                            wg_ld4(fk + D_EIN * 8, in.e0);
-                            wg_ld4(fk + (D_EIN + 4) * 8, in.e1);
+                            for (int l = 0; l < 4; ++l) wgf_ld4<PP>(fk, D_ACLIN + 4 * l, rp, in.ac[l]);
+                            wgf_ld2<PP>(fk, D_HIN, rp, in.h0[0], in.h0[1]);
+                            wgf_ld2<PP>(fk, D_HIN + 2, rp, in.h1[0], in.h1[1]);
+                            wgf_ld4<PP>(fk, D_EIN, rp, in.e0);
+                            wgf_ld4<PP>(fk, D_EIN + 4, rp, in.e1);
+                            if (PP) {                                   // operands are in registers: hand the slot back
+                                wg_arrive(rempty + 8u * sl);
+                                ++cstep;
+                            }
                             const uint32_t o = (uint32_t)(3 * k) * 8u;
 #pragma unroll
                             for (int e = 0; e < 2; ++e) { in.z[e] = wg_ld(zs + o + 8u * e); in.u[e] = wg_ld(us + o + 8u * e); }
@@ -354,17 +423,29 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                 double si[4] = {wg_ld(s0s), wg_ld(s0s + 8), wg_ld(s0s + 24), wg_ld(s0s + 32)};
                 {
                     struct In { double d[2], kn[2][4], an[4][4], bn[4][2]; };
-                    wg_stage_loop<In>(0, 1, N,
+                    wg_stage_loop<In, PP>(0, 1, N,
                         [&](int k, In &o) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u, dk = ds + (uint32_t)(3 * k) * 8u;
-                            wg_ld4(fk + D_KIN * 8, o.kn[0]);
-                            wg_ld4(fk + (D_KIN + 4) * 8, o.kn[1]);
+                            const uint32_t dk = ds + (uint32_t)(3 * k) * 8u;
+                            uint32_t fk, sl = 0;
+                            if (PP) {                                   // this stage's records: wait for the TMA box
+                                sl = cstep & (WG_PP_R - 1);
+                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                            } else {
+                                fk = fac_s + (uint32_t)(k * FW) * 8u;
+                            }
+                            wgf_ld4<PP>(fk, D_KIN, rp, o.kn[0]);
+                            wgf_ld4<PP>(fk, D_KIN + 4, rp, o.kn[1]);
                             if (!TI) {
 #pragma unroll
                                 for (int r = 0; r < 4; ++r) {
-                                    wg_ld4(fk + (D_AIN + 4 * r) * 8, o.an[r]);
-                                    wg_ld2(fk + (D_BIN + 2 * r) * 8, o.bn[r][0], o.bn[r][1]);
+                                    wgf_ld4<PP>(fk, D_AIN + 4 * r, rp, o.an[r]);
+                                    wgf_ld2<PP>(fk, D_BIN + 2 * r, rp, o.bn[r][0], o.bn[r][1]);
                                 }
+                            }
+                            if (PP) {                                   // operands are in registers: hand the slot back
+                                wg_arrive(rempty + 8u * sl);
+                                ++cstep;
                             }
                             o.d[0] = wg_ld(dk);
                             o.d[1] = wg_ld(dk + 8);
@@ -414,14 +495,25 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                 }
                 {
                     struct In { double z, u, hc[2], ec[2], kc[2], a0[2], a1[2]; };
-                    wg_stage_loop<In>(N - 1, -1, N,
+                    wg_stage_loop<In, PP>(N - 1, -1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
-                            wg_ld2(fk + D_KC * 8, in.kc[0], in.kc[1]);
-                            wg_ld2(fk + D_ACLC * 8, in.a0[0], in.a0[1]);
-                            wg_ld2(fk + (D_ACLC + 2) * 8, in.a1[0], in.a1[1]);
-                            wg_ld2(fk + D_HC * 8, in.hc[0], in.hc[1]);
-                            wg_ld2(fk + D_EC * 8, in.ec[0], in.ec[1]);
+                            uint32_t fk, sl = 0;
+                            if (PP) {                                   // this stage's records: wait for the TMA box
+                                sl = cstep & (WG_PP_R - 1);
+                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                            } else {
+                                fk = fac_s + (uint32_t)(k * FW) * 8u;
+                            }
+                            wgf_ld2<PP>(fk, D_KC, rp, in.kc[0], in.kc[1]);
+                            wgf_ld2<PP>(fk, D_ACLC, rp, in.a0[0], in.a0[1]);
+                            wgf_ld2<PP>(fk, D_ACLC + 2, rp, in.a1[0], in.a1[1]);
+                            wgf_ld2<PP>(fk, D_HC, rp, in.hc[0], in.hc[1]);
+                            wgf_ld2<PP>(fk, D_EC, rp, in.ec[0], in.ec[1]);
+                            if (PP) {                                   // operands are in registers: hand the slot back
+                                wg_arrive(rempty + 8u * sl);
+                                ++cstep;
+                            }
                             const uint32_t o = (uint32_t)(3 * k + 2) * 8u;
                             in.z = wg_ld(zs + o);
                             in.u = wg_ld(us + o);
@@ -443,14 +535,25 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                 double sc0 = wg_ld(s0s + 16), sc1 = wg_ld(s0s + 40);
                 {
                     struct In { double kc[2], a0[2], a1[2], bc[2], d2; };
-                    wg_stage_loop<In>(0, 1, N,
+                    wg_stage_loop<In, PP>(0, 1, N,
                         [&](int k, In &in) {
-                            const uint32_t fk = fac_s + (uint32_t)(k * FW) * 8u;
-                            wg_ld2(fk + D_KC * 8, in.kc[0], in.kc[1]);
+                            uint32_t fk, sl = 0;
+                            if (PP) {                                   // this stage's records: wait for the TMA box
+                                sl = cstep & (WG_PP_R - 1);
+                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                            } else {
+                                fk = fac_s + (uint32_t)(k * FW) * 8u;
+                            }
+                            wgf_ld2<PP>(fk, D_KC, rp, in.kc[0], in.kc[1]);
                             if (!TI) {
-                                wg_ld2(fk + D_AC * 8, in.a0[0], in.a0[1]);
-                                wg_ld2(fk + (D_AC + 2) * 8, in.a1[0], in.a1[1]);
-                                wg_ld2(fk + D_BC * 8, in.bc[0], in.bc[1]);
+                                wgf_ld2<PP>(fk, D_AC, rp, in.a0[0], in.a0[1]);
+                                wgf_ld2<PP>(fk, D_AC + 2, rp, in.a1[0], in.a1[1]);
+                                wgf_ld2<PP>(fk, D_BC, rp, in.bc[0], in.bc[1]);
+                            }
+                            if (PP) {                                   // operands are in registers: hand the slot back
+                                wg_arrive(rempty + 8u * sl);
+                                ++cstep;
                             }
                             in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
                         },
@@ -532,6 +635,28 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW)
                     WG_TK(1, k);
                 }
                 WG_T(3);
+            } else if (PP && warp == 4) {
+                // ================= per-problem models: the records of the 2 N sweep stages of this iteration, in the order
+                // the chain warps consume them (backward N-1 .. 0, forward 0 .. N-1), WG_PP_R - 1 stages ahead of them at most
+                const int col0 = tile * TW;
+                for (int q = 0; q < 2 * N; ++q) {
+                    const uint32_t sl = pstep & (WG_PP_R - 1);
+                    wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
+                    if ((tid & 31) == 0) {
+                        const uint32_t dst = ring_s + sl * slot_bytes, bar = rfull + 8u * sl;
+                        if (q < N) {
+                            const int k = N - 1 - q;
+                            mbar_expect_tx(bar, (uint32_t)WG_PP_ROWS * rp);
+                            wg_tma(dst, &maps.mB, col0, k * FD, bar);
+                        } else {
+                            const int k = q - N;
+                            mbar_expect_tx(bar, 40u * rp);
+                            wg_tma(dst, &maps.mF0, col0, k * FD, bar);
+                            wg_tma(dst + 10u * rp, &maps.mF1, col0, k * FD + D_AIN, bar);
+                        }
+                    }
+                    ++pstep;
+                }
             } else if (norms) {
                 // ================= the five norm accumulators, blocks in the oracle's order, behind the prox warps
                 double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
