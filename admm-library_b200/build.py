@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "admm_b200.cu")
 # translation units: the host library + three thirds of the persistent-kernel template variants
-UNITS = ["admm_b200.cu", "iter_smem.cu", "iter_gshared.cu", "iter_pp.cu", "iter_pptma.cu", "iter_res.cu", "iter_wg.cu", "iter_pint.cu"]
+UNITS = ["admm_b200.cu", "iter_smem.cu", "iter_gshared.cu", "iter_pp.cu", "iter_pptma.cu", "iter_res.cu", "iter_wg.cu", "iter_wgpp.cu", "iter_pint.cu"]
 OUT_DIR = os.path.join(HERE, os.environ.get("ADMMB_BUILD_DIR", "lib"))   # developer builds may go elsewhere
 OUT = os.path.join(OUT_DIR, "libadmm_b200.so")
 

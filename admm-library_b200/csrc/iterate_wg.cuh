@@ -37,7 +37,15 @@ constexpr int WG_WARPS = 8;
 // PP (per-problem models, config 4): the stage records of the tile's problems are streamed through a ring of WG_PP_R
 // shared-memory slots by TMA (one box of [record rows] x [TW columns] per sweep stage, issued by warp 4, which is
 // otherwise idle) instead of being read from a shared factor table; full / empty mbarriers per slot.
-constexpr int WG_PP_R = 8;                       // ring slots (power of two)
+#ifndef WG_PP_RING
+#define WG_PP_RING 8
+#endif
+constexpr int WG_PP_R = WG_PP_RING;               // ring slots (power of two; -DWG_PP_RING=n: developer builds)
+#ifndef WG_PP_CPASYNC
+constexpr int WG_PP_FULL_COUNT = 1;              // full barrier: the producer's expect_tx arrival (+ the TMA bytes)
+#else
+constexpr int WG_PP_FULL_COUNT = 32;             // full barrier: one cp.async completion arrival per producer lane
+#endif
 constexpr int WG_PP_ROWS = D_AIN;                // rows of a slot: a backward stage needs record rows 0..45, a forward stage 10 + 30
 struct WgPpMaps {
     CUtensorMap mB, mF0, mF1;                    // boxes of 46 / 10 / 30 rows x TW columns over fac_dec [FD*N][ld]
@@ -169,6 +177,9 @@ __device__ __forceinline__ void wg_wait_spin(uint32_t bar, uint32_t parity)
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#ifdef WG_SPIN_BACKOFF
+        if (!ok) __nanosleep(WG_SPIN_BACKOFF);
+#endif
         if (!ok && ++spins > (1 << 24)) __trap();
     } while (!ok);
 }
@@ -176,11 +187,23 @@ __device__ __forceinline__ void wg_wait_spin(uint32_t bar, uint32_t parity)
 // Stage loop with the operands of the next stage loaded (into registers) BEFORE the current stage's arithmetic and
 // stores: a warp issues in order, so without this every stage would start by waiting out its own load latency.
 // Stage j = 0 .. count-1 is k = k0 + j * stride.  Branch-free body: the prefetch past the end re-reads the last stage.
-// EXACT: every stage is loaded exactly once (a load consumes a ring slot: PP), at the price of one branch per pair of stages.
+// EXACT (PP): every stage is loaded exactly once (a load consumes a ring slot), straight before its arithmetic.
 template <class In, bool EXACT = false, class LoadFn, class WorkFn>
 __device__ __forceinline__ void wg_stage_loop(const int k0, const int stride, const int count, LoadFn load, WorkFn work)
 {
     if (count <= 0) return;
+    if (EXACT) {
+        // PP: the operands already wait in shared memory (the TMA ring IS the prefetch), so one register copy of a stage is
+        // enough.  Two copies (80 doubles) next to the chain state took all 255 registers: spills and 44 register moves
+        // inside every pair of stages, 240 instead of 105 instructions per stage on a warp that issues one per 2.3 cycles.
+        int k = k0;
+        for (int j = 0; j < count; ++j, k += stride) {
+            In a;
+            load(k, a);
+            work(k, a);
+        }
+        return;
+    }
     In a, b;
     load(k0, a);
     const int klast = k0 + (count - 1) * stride;
@@ -188,8 +211,7 @@ __device__ __forceinline__ void wg_stage_loop(const int k0, const int stride, co
     for (int j = 0; j + 1 < count; j += 2, k += 2 * stride) {
         load(k + stride, b);
         work(k, a);
-        if (EXACT) { if (j + 2 < count) load(k + 2 * stride, a); }
-        else load(j + 2 < count ? k + 2 * stride : klast, a);
+        load(j + 2 < count ? k + 2 * stride : klast, a);
         work(k + stride, b);
     }
     if (count & 1) work(klast, a);
@@ -208,11 +230,17 @@ __device__ long long wg_klog[3][64];               // per stage: a_k published (
 
 // TI: A_k, B_k do not depend on the stage (time-invariant dynamics, e.g. Clohessy-Wiltshire with a fixed step): the chain
 // warps keep them in registers for the whole launch instead of re-reading 30 doubles per stage on the forward sweep
-template <bool ADAPT, bool TI, bool PP = false>
+// PTW (PP only): the tile width as a compile-time constant.  A ring slot is [record rows] x [TW columns], so the row pitch
+// of every operand load of the chain warps is TW * 8 bytes: with a run-time TW each of the 46 + 40 loads of a stage pair
+// needed its own IMAD and address register (255 registers, spills inside the sweep loops, 240 instructions per stage);
+// as a constant they are immediates off one base register.
+template <bool ADAPT, bool TI, bool PP = false, int PTW = 0>
 __global__ void __launch_bounds__(WG_WARPS * 32, 1)
-k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW, const __grid_constant__ WgPpMaps maps)
+k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const __grid_constant__ WgPpMaps maps)
 {
     static_assert(!(TI && PP), "per-problem models are not time-invariant");
+    static_assert(PP == (PTW > 0) && PTW % 8 == 0, "the streamed-record form is instantiated per tile width (8, 16, 24, 32)");
+    const int TW = PTW > 0 ? PTW : TW_arg;
     extern __shared__ __align__(128) unsigned char wg_smem[];
     const int N = P.N;
     constexpr int FW = PP ? 0 : (TI ? D_AIN : FD);       // stage pitch of the factor copy in shared memory (see wg_layout)
@@ -249,7 +277,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW, const __gr
         for (int k = 0; k <= N; ++k) mbar_init(bC2 + 8u * k, 2);      // both chain warps
         for (int w = 0; w < WG_PROX; ++w) asm volatile("st.shared.u32 [%0], %1;" ::"r"(prog_s + 4u * w), "r"(0) : "memory");
         if (PP) {
-            for (int i = 0; i < WG_PP_R; ++i) { mbar_init(rfull + 8u * i, 1); mbar_init(rempty + 8u * i, 2); }
+            for (int i = 0; i < WG_PP_R; ++i) { mbar_init(rfull + 8u * i, WG_PP_FULL_COUNT); mbar_init(rempty + 8u * i, 2); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -639,6 +667,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW, const __gr
                 // ================= per-problem models: the records of the 2 N sweep stages of this iteration, in the order
                 // the chain warps consume them (backward N-1 .. 0, forward 0 .. N-1), WG_PP_R - 1 stages ahead of them at most
                 const int col0 = tile * TW;
+#ifndef WG_PP_CPASYNC
                 for (int q = 0; q < 2 * N; ++q) {
                     const uint32_t sl = pstep & (WG_PP_R - 1);
                     wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
@@ -657,6 +686,33 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW, const __gr
                     }
                     ++pstep;
                 }
+#else
+                // developer build (-DWG_PP_CPASYNC), measured and dropped: 16-byte cp.async copies by all 32 lanes, completion
+                // reported to the slot's full barrier by every lane (cp.async.mbarrier.arrive.noinc: the barrier counts 32
+                // arrivals) -- 94 us per iteration against 25.9 with the TMA boxes (2,200 cycles per backward stage).
+                constexpr int CPR = PTW > 0 ? PTW / 2 : 1;                         // 16-byte chunks per row of a slot
+                const int ln = tid & 31;
+                for (int q = 0; q < 2 * N; ++q) {
+                    const uint32_t sl = pstep & (WG_PP_R - 1);
+                    wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
+                    const uint32_t dst = ring_s + sl * slot_bytes, bar = rfull + 8u * sl;
+                    const bool bwd = q < N;
+                    const int k = bwd ? N - 1 - q : q - N;
+                    const int nrows = bwd ? WG_PP_ROWS : 40;
+                    const double *src = P.fac_dec + (size_t)(k * FD) * ld;
+#pragma unroll 4
+                    for (int i = ln; i < nrows * CPR; i += 32) {
+                        const int r = i / CPR, c = i - r * CPR;                    // slot row, chunk of the row
+                        const int rr = (bwd || r < 10) ? r : r + 36;               // record row: a forward slot is K, then A, B (rows 46 .. 75)
+                        const int col = col0 + 2 * c;
+                        if ((size_t)col + 2 <= ld)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)r * rp + 16u * c),
+                                         "l"(src + (size_t)rr * ld + col) : "memory");
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+                    ++pstep;
+                }
+#endif
             } else if (norms) {
                 // ================= the five norm accumulators, blocks in the oracle's order, behind the prox warps
                 double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;

@@ -373,6 +373,20 @@ def test_per_problem_models_wide_working_set(solver, cpu_oracle, P, coupled, ker
     assert_bit_identical(got, ref, f"4,800 per-problem models, coupled={coupled}")
 
 
+# ---- per-problem decoupled models on the streamed-record warp-group kernel at other horizons: the tile width follows the
+# shared memory left next to the TMA ring (32 problems at N = 20, 24 at N = 50, 8 at N = 100) and has to keep every TMA box
+# on a 128-byte boundary (multiples of 8 only: a 14-problem tile at N = 100 faulted with a misaligned address in round 2);
+# ragged batches, so the last tile is padded with copies of its last lane.
+@pytest.mark.parametrize("N,batch", [(7, 45), (20, 70), (33, 100), (100, 21)])
+def test_per_problem_models_warp_group_horizons(solver, cpu_oracle, P, N, batch, kernel_variant):
+    if kernel_variant not in ("auto", "wg"):
+        pytest.skip("the streamed-record warp-group kernel runs when pinned or on narrow working sets")
+    prob, opts = P.cfg4_elliptic(batch=batch, N=N, seed=40 + N)
+    opts = dict(opts, max_iter=250, history=1)
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    assert_bit_identical(got, ref, f"per-problem models, N={N}, batch={batch}")
+
+
 # ---- receding-horizon step on the resident batch: admmb_shift_resolve against the oracle's warm-started solve
 @pytest.mark.parametrize("k,from_solution", [(1, True), (1, False), (3, False)])
 def test_shift_resolve_matches_oracle_warm_start(pkg, cpu_oracle, P, k, from_solution, kernel_variant):
