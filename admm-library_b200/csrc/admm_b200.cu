@@ -187,6 +187,7 @@ struct Shard {
                         DevBuf<double> &par_e, DevBuf<double> &par_th);
     DevBuf<double> gen_e, gen_th;
     DevBuf<double> pint_tab;          // parallel-in-time kernel: tables of the current shared factor (iterate_pint.cuh)
+    DevBuf<double> wgpp_blk;          // streamed-record warp-group kernel: tile-blocked copy of the per-problem records (iterate_wg.cuh)
     bool pint_ready = false;
     void run(const admmb_opts *op, admmb_result *res);
     void download(admmb_result *res);
@@ -391,7 +392,9 @@ static bool wg_takes(int64_t n_active, int tile, int num_sms)
 // passes (tiles per CTA), measured against k_admm_iterate_pptma (scripts/variant_rates.py cfg4); ADMMB_WGPP_PASSES overrides
 static bool wgpp_takes(int64_t n_active, int tile, int num_sms)
 {
-    static const int64_t max_passes = getenv("ADMMB_WGPP_PASSES") ? atoll(getenv("ADMMB_WGPP_PASSES")) : 2;
+    // measured (profiles/r2_cfg4_variant_rates.txt, N = 50, 24-problem tiles): 8,192 problems = 3 passes 73 vs 92 us per iteration,
+    // 12,288 = 4 passes 98 vs 104, 16,384 = 5 passes 133 vs 118
+    static const int64_t max_passes = getenv("ADMMB_WGPP_PASSES") ? atoll(getenv("ADMMB_WGPP_PASSES")) : 3;
     const int64_t tiles = (n_active + tile - 1) / tile;
     return (tiles + num_sms - 1) / num_sms <= max_passes;
 }
@@ -417,6 +420,10 @@ void Shard::launch_iterate(const IterParams &P, bool adapt)
         // working sets, where one problem per thread is bound by a lone warp's instruction stream (52-70 us per iteration)
         const int tw = iterate_wgpp_tile_width(c, adapt && P.has_P);
         const bool wgpp = tw > 0 && (kernel_variant == KV_WG || (kernel_variant == KV_AUTO && wgpp_takes(P.n_active, tw, num_sms)));
+        if (wgpp) {                         // room for the tile-blocked copy of the records (grows on first use only)
+            wgpp_blk.alloc(wgpp_block_doubles(c, P.n_active, tw));
+            c.wgpp_blk = wgpp_blk.p;
+        }
         if (wgpp && launch_iterate_wgpp(c, P, adapt)) last_kernel = KV_WG;
         else if (!launch_iterate_pptma(c, P, adapt)) launch_iterate_pp(c, P, adapt);
     }

@@ -25,6 +25,12 @@ int iterate_wgpp_tile_width(const IterLaunchCtx &c, bool refactors)
     return 0;
 }
 
+size_t wgpp_block_doubles(const IterLaunchCtx &c, int n_active, int tw)
+{
+    const size_t ntiles = ((size_t)n_active + tw - 1) / tw;
+    return ntiles * (size_t)c.N * WG_PP_BLK_ROWS * tw;
+}
+
 bool launch_iterate_wgpp(const IterLaunchCtx &c, const IterParams &P, bool adapt)
 {
     const int tw = iterate_wgpp_tile_width(c, adapt && P.has_P);
@@ -34,12 +40,17 @@ bool launch_iterate_wgpp(const IterLaunchCtx &c, const IterParams &P, bool adapt
     const int grid = ntiles < c.num_sms ? ntiles : c.num_sms;
     const size_t rows = (size_t)FD * c.N;
     WgPpMaps maps = {};
-#ifndef WG_PP_CPASYNC
+#ifdef WG_PP_TMA_BOXES
     maps.mB = tmap_box_f64(P.fac_dec, rows, P.ld, WG_PP_ROWS, (uint32_t)tw);
     maps.mF0 = tmap_box_f64(P.fac_dec, rows, P.ld, 10, (uint32_t)tw);
     maps.mF1 = tmap_box_f64(P.fac_dec, rows, P.ld, 30, (uint32_t)tw);
 #else
+    // the records of this launch's working set, tile by tile (a repack between launches moves columns, so the copy is made
+    // per launch: one pass over the records, a few per cent of a launch of 50+ iterations)
     (void)rows;
+    if (!c.wgpp_blk) return false;
+    k_wgpp_block<<<dim3((unsigned)ntiles, (unsigned)c.N), 256, 0, c.stream>>>(P.fac_dec, P.ld, c.N, P.n_active, tw, c.wgpp_blk);
+    maps.blk = c.wgpp_blk;
 #endif
 #define WGPP_LAUNCH(A, W)                                                                              \
     do {                                                                                               \

@@ -13,6 +13,8 @@ struct IterLaunchCtx {
     int device;
     bool time_invariant;          // shared model whose A_k, B_k are the same for every stage (bitwise)
     const double *pint_table;     // parallel-in-time kernel: correction / transition tables of the current factor (or null)
+    double *wgpp_blk = nullptr;   // streamed-record warp-group kernel: room for the tile-blocked copy of the stage records
+                                  // (wgpp_block_doubles() doubles, owned by the shard), or null
 };
 void launch_iterate_smem(const IterLaunchCtx &c, const IterParams &P, bool adapt);
 void launch_iterate_gshared(const IterLaunchCtx &c, const IterParams &P, bool adapt);
@@ -30,6 +32,7 @@ int iterate_wg_tile_width(const IterLaunchCtx &c);
 // the same kernel for per-problem decoupled models: stage records streamed through a TMA ring; refactors: a rho change would
 // need a new factor inside the kernel (adaptive rho with a quadratic cost), which this form does not do
 bool launch_iterate_wgpp(const IterLaunchCtx &c, const IterParams &P, bool adapt);
+size_t wgpp_block_doubles(const IterLaunchCtx &c, int n_active, int tw);
 int iterate_wgpp_tile_width(const IterLaunchCtx &c, bool refactors);
 // parallel-in-time kernel (iterate_pint.cuh): eight warps sweep eight chunks of stages at the same time;
 // same eligibility as the warp-group kernel; FP64 but not the oracle's operation order, hence opt-in (KV_PINT) only

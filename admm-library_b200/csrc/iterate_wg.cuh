@@ -49,7 +49,26 @@ constexpr int WG_PP_FULL_COUNT = 32;             // full barrier: one cp.async c
 constexpr int WG_PP_ROWS = D_AIN;                // rows of a slot: a backward stage needs record rows 0..45, a forward stage 10 + 30
 struct WgPpMaps {
     CUtensorMap mB, mF0, mF1;                    // boxes of 46 / 10 / 30 rows x TW columns over fac_dec [FD*N][ld]
+    const double *blk;                           // tile-blocked copy of the records (k_wgpp_block), the default source
 };
+// Tile-blocked copy of the per-problem stage records: [tile][stage][WG_PP_BLK_ROWS rows][TW columns], rows 0..45 = what a
+// backward stage reads (record rows 0..45: K, Acl, Hinv, E), rows 46..85 = what a forward stage reads (K again: 10 rows, then
+// A, B: record rows 46..75).  One ring slot is then ONE contiguous bulk copy (cp.async.bulk, 8.8 KB at TW = 24) instead of a
+// TMA box of 46 strided rows: the TMA unit took ~9.5 cycles per row of a box whatever the row length, ring depth or the
+// chain's own work (510 cycles per stage, profiles/r2_wgpp_timeline.txt).
+constexpr int WG_PP_BLK_ROWS = D_AIN + 40;
+static __global__ void k_wgpp_block(const double *__restrict__ fac_dec, size_t ld, int N, int n_active, int TW, double *__restrict__ blk)
+{
+    const int tile = blockIdx.x, k = blockIdx.y;
+    const double *src = fac_dec + (size_t)(k * FD) * ld;
+    double *dst = blk + ((size_t)tile * N + k) * WG_PP_BLK_ROWS * TW;
+    for (int i = threadIdx.x; i < WG_PP_BLK_ROWS * TW; i += blockDim.x) {
+        const int r = i / TW, c = i - r * TW;
+        const int rr = r < D_AIN ? r : (r < D_AIN + 10 ? r - D_AIN : r - 10);     // record row
+        const int col = min(tile * TW + c, n_active - 1);                        // columns past the batch: copies of its last problem
+        dst[i] = __ldcg(src + (size_t)rr * ld + col);
+    }
+}
 constexpr int WG_MIN_TW = 8;                     // narrower tiles waste more than 3/4 of every warp: not worth it
 constexpr int WG_PROX = 4;                       // prox warps
 
@@ -167,6 +186,16 @@ __device__ __forceinline__ void wg_wait(uint32_t bar, uint32_t parity)
     } while (!ok);
 }
 
+// One non-blocking test of a barrier phase (the result is used a stage later: see pre_ok in the kernel)
+__device__ __forceinline__ uint32_t wg_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
 // Same hand-over, polled with test_wait: a try_wait that has to block suspends the warp and wakes it up late; the prox warps
 // sit right behind the chain, where that wake-up latency goes straight into the length of an iteration.
 __device__ __forceinline__ void wg_wait_spin(uint32_t bar, uint32_t parity)
@@ -271,6 +300,9 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
     const uint32_t rfull = sm0 + (uint32_t)L.rbar, rempty = rfull + 8u * WG_PP_R, ring_s = sm0 + (uint32_t)L.ring;
     const uint32_t rp = (uint32_t)TW * 8u;               // row pitch of a slot
     const uint32_t slot_bytes = (uint32_t)WG_PP_ROWS * rp;
+    // PP, chain warps: the NEXT slot's full barrier is tested right after a stage's operands have been read, so the ~100-cycle
+    // round trip of the test runs under that stage's arithmetic instead of in front of the next stage's loads
+    uint32_t pre_ok = 0;
     uint32_t cstep = 0, pstep = 0;                       // ring steps consumed (chain warps) / produced (warp 4) since the launch began
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -394,9 +426,12 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                     wg_stage_loop<In, PP>(N - 1, -1, N,
                         [&](int k, In &in) {
                             uint32_t fk, sl = 0;
-                            if (PP) {                                   // this stage's records: wait for the TMA box
+                            if (PP) {                                   // this stage's records: wait for the slot
+                                const uint32_t o = (uint32_t)(3 * k) * 8u;  // (z, u first: they do not wait for the ring)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) { in.z[e] = wg_ld(zs + o + 8u * e); in.u[e] = wg_ld(us + o + 8u * e); }
                                 sl = cstep & (WG_PP_R - 1);
-                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
                                 fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
@@ -412,10 +447,13 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                             if (PP) {                                   // operands are in registers: hand the slot back
                                 wg_arrive(rempty + 8u * sl);
                                 ++cstep;
+                                pre_ok = wg_test(rfull + 8u * (cstep & (WG_PP_R - 1)), (cstep / WG_PP_R) & 1u);
                             }
-                            const uint32_t o = (uint32_t)(3 * k) * 8u;
+                            if (!PP) {
+                                const uint32_t o = (uint32_t)(3 * k) * 8u;
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) { in.z[e] = wg_ld(zs + o + 8u * e); in.u[e] = wg_ld(us + o + 8u * e); }
+                                for (int e = 0; e < 2; ++e) { in.z[e] = wg_ld(zs + o + 8u * e); in.u[e] = wg_ld(us + o + 8u * e); }
+                            }
                         },
                         [&](int k, const In &in) {
                             double ra[2];
@@ -455,9 +493,11 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                         [&](int k, In &o) {
                             const uint32_t dk = ds + (uint32_t)(3 * k) * 8u;
                             uint32_t fk, sl = 0;
-                            if (PP) {                                   // this stage's records: wait for the TMA box
+                            if (PP) {                                   // this stage's records: wait for the slot
+                                o.d[0] = wg_ld(dk);
+                                o.d[1] = wg_ld(dk + 8);
                                 sl = cstep & (WG_PP_R - 1);
-                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
                                 fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
@@ -474,9 +514,12 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                             if (PP) {                                   // operands are in registers: hand the slot back
                                 wg_arrive(rempty + 8u * sl);
                                 ++cstep;
+                                pre_ok = wg_test(rfull + 8u * (cstep & (WG_PP_R - 1)), (cstep / WG_PP_R) & 1u);
                             }
-                            o.d[0] = wg_ld(dk);
-                            o.d[1] = wg_ld(dk + 8);
+                            if (!PP) {
+                                o.d[0] = wg_ld(dk);
+                                o.d[1] = wg_ld(dk + 8);
+                            }
                         },
                         [&](int k, const In &o) {
                             double a0 = o.d[0], a1 = o.d[1];
@@ -526,9 +569,12 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                     wg_stage_loop<In, PP>(N - 1, -1, N,
                         [&](int k, In &in) {
                             uint32_t fk, sl = 0;
-                            if (PP) {                                   // this stage's records: wait for the TMA box
+                            if (PP) {                                   // this stage's records: wait for the slot
+                                const uint32_t o = (uint32_t)(3 * k + 2) * 8u;
+                                in.z = wg_ld(zs + o);
+                                in.u = wg_ld(us + o);
                                 sl = cstep & (WG_PP_R - 1);
-                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
                                 fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
@@ -541,10 +587,13 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                             if (PP) {                                   // operands are in registers: hand the slot back
                                 wg_arrive(rempty + 8u * sl);
                                 ++cstep;
+                                pre_ok = wg_test(rfull + 8u * (cstep & (WG_PP_R - 1)), (cstep / WG_PP_R) & 1u);
                             }
-                            const uint32_t o = (uint32_t)(3 * k + 2) * 8u;
-                            in.z = wg_ld(zs + o);
-                            in.u = wg_ld(us + o);
+                            if (!PP) {
+                                const uint32_t o = (uint32_t)(3 * k + 2) * 8u;
+                                in.z = wg_ld(zs + o);
+                                in.u = wg_ld(us + o);
+                            }
                         },
                         [&](int k, const In &in) {
                             const double uu = ADAPT ? in.u * sigma : in.u;
@@ -566,9 +615,10 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                     wg_stage_loop<In, PP>(0, 1, N,
                         [&](int k, In &in) {
                             uint32_t fk, sl = 0;
-                            if (PP) {                                   // this stage's records: wait for the TMA box
+                            if (PP) {                                   // this stage's records: wait for the slot
+                                in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
                                 sl = cstep & (WG_PP_R - 1);
-                                wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
+                                if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
                                 fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
@@ -582,8 +632,9 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                             if (PP) {                                   // operands are in registers: hand the slot back
                                 wg_arrive(rempty + 8u * sl);
                                 ++cstep;
+                                pre_ok = wg_test(rfull + 8u * (cstep & (WG_PP_R - 1)), (cstep / WG_PP_R) & 1u);
                             }
-                            in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
+                            if (!PP) in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
                         },
                         [&](int k, const In &in) {
                             double a2 = fma(in.kc[0], sc0, in.d2);
@@ -667,12 +718,14 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                 // ================= per-problem models: the records of the 2 N sweep stages of this iteration, in the order
                 // the chain warps consume them (backward N-1 .. 0, forward 0 .. N-1), WG_PP_R - 1 stages ahead of them at most
                 const int col0 = tile * TW;
+                (void)col0;
 #ifndef WG_PP_CPASYNC
                 for (int q = 0; q < 2 * N; ++q) {
                     const uint32_t sl = pstep & (WG_PP_R - 1);
                     wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
                     if ((tid & 31) == 0) {
                         const uint32_t dst = ring_s + sl * slot_bytes, bar = rfull + 8u * sl;
+#ifdef WG_PP_TMA_BOXES      // developer build: the slots filled by TMA boxes straight from fac_dec (A/B of DESIGN 4.10)
                         if (q < N) {
                             const int k = N - 1 - q;
                             mbar_expect_tx(bar, (uint32_t)WG_PP_ROWS * rp);
@@ -683,6 +736,14 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                             wg_tma(dst, &maps.mF0, col0, k * FD, bar);
                             wg_tma(dst + 10u * rp, &maps.mF1, col0, k * FD + D_AIN, bar);
                         }
+#else
+                        const bool bwd = q < N;
+                        const int k = bwd ? N - 1 - q : q - N;
+                        const double *src = maps.blk + (((size_t)tile * N + k) * WG_PP_BLK_ROWS + (bwd ? 0 : D_AIN)) * TW;
+                        const uint32_t bytes = (bwd ? (uint32_t)WG_PP_ROWS : 40u) * rp;
+                        mbar_expect_tx(bar, bytes);
+                        bulk_g2s(dst, src, bytes, bar);
+#endif
                     }
                     ++pstep;
                 }

@@ -499,8 +499,8 @@ def main():
         configs = {}
         kernels = {"cfg2": "k_admm_iterate_wg (4,096 <= 14,208 running problems from the start)",
                    "cfg3": "k_admm_iterate_wg (N = 100: 15 problems per resident tile)",
-                   "cfg4": "k_admm_iterate_pptma above two tiles per SM (one problem per thread, records streamed by TMA), "
-                           "k_admm_iterate_wg<PP> below (24-problem resident tiles, records through an eight-slot TMA ring)",
+                   "cfg4": "k_admm_iterate_pptma above three tiles per SM (one problem per thread, records streamed by TMA), "
+                           "k_admm_iterate_wg<PP> below (24-problem resident tiles, tile-blocked records through an eight-slot bulk-copy ring)",
                    "cfg5": "k_admm_iterate2 / k_admm_iterate, k_admm_iterate_wg below 14,208 running problems (adaptive rho)"}
         t_cfg0 = time.perf_counter()
         for cname in ("cfg2", "cfg3", "cfg4", "cfg5"):

@@ -3,7 +3,7 @@
 # (-DWG_PP_RING=n into lib_r<n>/) and the per-warp cycle timeline of one iteration (-DWG_TIMING build in lib_timing/)
 tag=${1:-ring}
 mkdir -p gpurun_out
-for lib in lib lib_r4 lib_r16 lib_bo; do
+for lib in lib lib_r4 lib_r16; do
     [ -f admm-library_b200/$lib/libadmm_b200.so ] || continue
     echo "== $lib" >> gpurun_out/rates_$tag.log
     ADMMB_LIB=admm-library_b200/$lib/libadmm_b200.so timeout 200 python scripts/variant_rates.py cfg4 200 100 64,2048,4096 wg >> gpurun_out/rates_$tag.log 2>&1
