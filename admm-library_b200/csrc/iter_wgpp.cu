@@ -2,7 +2,6 @@
 // tile are streamed through a TMA ring; one instantiation per tile width (8, 16, 24, 32 problems).
 #include <cstdlib>
 #include "host_util.cuh"
-#include "tma_host.cuh"
 #define ADMMB_ITERATE_ONLY
 #include "iterate_wg.cuh"
 #include "iterate_launch_decl.cuh"
@@ -11,15 +10,15 @@
 namespace admmb {
 
 // ---- per-problem models (config 4): the same kernel with the stage records streamed through a TMA ring (iterate_wg.cuh, PP)
-// widest tile of 8, 16, 24 or 32 problems whose z, u, d, g rows fit next to the ring; 0: not eligible.  Multiples of 8 only:
-// a TMA box lands on a 128-byte boundary, and both the slots (46 rows x TW x 8 bytes) and the second box of a forward slot
-// (10 rows in) keep that alignment exactly when TW is a multiple of 8.  A rho change must not need a new factor
+// widest tile of 8, 16, 24 or 32 problems whose z, u, d, g rows fit next to the ring; 0: not eligible.  Multiples of 8: one
+// instantiation per width (the first form, TMA boxes, needed them for the 128-byte alignment of every box; a bulk copy needs
+// 16 bytes, which any even width gives).  A rho change must not need a new factor
 // (no quadratic cost), the affine term / linear cost / per-problem parameters are not handled (as in the shared-factor form).
 int iterate_wgpp_tile_width(const IterLaunchCtx &c, bool refactors)
 {
     if (!c.fast_pattern || !c.decoupled || c.has_c || c.has_q || c.par_batched || c.rows_zu <= 0 || refactors) return 0;
     static const int tw_cap = getenv("ADMMB_WG_TW") ? atoi(getenv("ADMMB_WG_TW")) : 32;
-    static_assert(WG_MIN_TW % 8 == 0 && (WG_PP_ROWS * 8 * 8) % 128 == 0 && (10 * 8 * 8) % 128 == 0, "TMA destinations of the ring");
+    static_assert(WG_MIN_TW % 8 == 0, "instantiated widths");
     for (int tw = (tw_cap < 32 ? tw_cap : 32) & ~7; tw >= WG_MIN_TW; tw -= 8)
         if (wg_layout(c.N, c.rows_zu, tw, 0, true).total <= WG_SMEM_MAX) return tw;
     return 0;
@@ -38,20 +37,11 @@ bool launch_iterate_wgpp(const IterLaunchCtx &c, const IterParams &P, bool adapt
     const size_t smem = wg_layout(c.N, c.rows_zu, tw, 0, true).total;
     const int ntiles = (P.n_active + tw - 1) / tw;
     const int grid = ntiles < c.num_sms ? ntiles : c.num_sms;
-    const size_t rows = (size_t)FD * c.N;
-    WgPpMaps maps = {};
-#ifdef WG_PP_TMA_BOXES
-    maps.mB = tmap_box_f64(P.fac_dec, rows, P.ld, WG_PP_ROWS, (uint32_t)tw);
-    maps.mF0 = tmap_box_f64(P.fac_dec, rows, P.ld, 10, (uint32_t)tw);
-    maps.mF1 = tmap_box_f64(P.fac_dec, rows, P.ld, 30, (uint32_t)tw);
-#else
     // the records of this launch's working set, tile by tile (a repack between launches moves columns, so the copy is made
     // per launch: one pass over the records, a few per cent of a launch of 50+ iterations)
-    (void)rows;
     if (!c.wgpp_blk) return false;
     k_wgpp_block<<<dim3((unsigned)ntiles, (unsigned)c.N), 256, 0, c.stream>>>(P.fac_dec, P.ld, c.N, P.n_active, tw, c.wgpp_blk);
-    maps.blk = c.wgpp_blk;
-#endif
+    WgPpMaps maps = {c.wgpp_blk};
 #define WGPP_LAUNCH(A, W)                                                                              \
     do {                                                                                               \
         wg_set_attr(k_admm_iterate_wg<A, false, true, W>, smem, c.device);                             \

@@ -28,7 +28,6 @@
 #ifdef WG_TIMING
 #include <cstdio>
 #endif
-#include <cuda.h>
 #include "kernels.cuh"
 
 namespace admmb {
@@ -41,21 +40,16 @@ constexpr int WG_WARPS = 8;
 #define WG_PP_RING 8
 #endif
 constexpr int WG_PP_R = WG_PP_RING;               // ring slots (power of two; -DWG_PP_RING=n: developer builds)
-#ifndef WG_PP_CPASYNC
-constexpr int WG_PP_FULL_COUNT = 1;              // full barrier: the producer's expect_tx arrival (+ the TMA bytes)
-#else
-constexpr int WG_PP_FULL_COUNT = 32;             // full barrier: one cp.async completion arrival per producer lane
-#endif
+constexpr int WG_PP_FULL_COUNT = 1;               // full barrier: the producer's expect_tx arrival (+ the bulk copy's bytes)
 constexpr int WG_PP_ROWS = D_AIN;                // rows of a slot: a backward stage needs record rows 0..45, a forward stage 10 + 30
 struct WgPpMaps {
-    CUtensorMap mB, mF0, mF1;                    // boxes of 46 / 10 / 30 rows x TW columns over fac_dec [FD*N][ld]
-    const double *blk;                           // tile-blocked copy of the records (k_wgpp_block), the default source
+    const double *blk;                           // tile-blocked copy of the records (k_wgpp_block)
 };
 // Tile-blocked copy of the per-problem stage records: [tile][stage][WG_PP_BLK_ROWS rows][TW columns], rows 0..45 = what a
 // backward stage reads (record rows 0..45: K, Acl, Hinv, E), rows 46..85 = what a forward stage reads (K again: 10 rows, then
 // A, B: record rows 46..75).  One ring slot is then ONE contiguous bulk copy (cp.async.bulk, 8.8 KB at TW = 24) instead of a
-// TMA box of 46 strided rows: the TMA unit took ~9.5 cycles per row of a box whatever the row length, ring depth or the
-// chain's own work (510 cycles per stage, profiles/r2_wgpp_timeline.txt).
+// TMA box of 46 strided rows.  Rows are interleaved in PAIRS -- element (r, c) at ((r / 2) * TW + c) * 2 + (r & 1) -- so that
+// a lane reads two consecutive record entries of its problem with one LDS.128 (every operand group starts on an even row).
 constexpr int WG_PP_BLK_ROWS = D_AIN + 40;
 static __global__ void k_wgpp_block(const double *__restrict__ fac_dec, size_t ld, int N, int n_active, int TW, double *__restrict__ blk)
 {
@@ -66,7 +60,7 @@ static __global__ void k_wgpp_block(const double *__restrict__ fac_dec, size_t l
         const int r = i / TW, c = i - r * TW;
         const int rr = r < D_AIN ? r : (r < D_AIN + 10 ? r - D_AIN : r - 10);     // record row
         const int col = min(tile * TW + c, n_active - 1);                        // columns past the batch: copies of its last problem
-        dst[i] = __ldcg(src + (size_t)rr * ld + col);
+        dst[((size_t)(r >> 1) * TW + c) * 2 + (r & 1)] = __ldcg(src + (size_t)rr * ld + col);
     }
 }
 constexpr int WG_MIN_TW = 8;                     // narrower tiles waste more than 3/4 of every warp: not worth it
@@ -140,30 +134,21 @@ __device__ __forceinline__ void wg_ld4(uint32_t a, double (&r)[4])
 }
 
 // Factor entries `off .. off+3` of the current stage.  Shared table: fk = address of the stage's record, one broadcast
-// 128-bit load per pair.  PP: fk = address of this lane's column in the ring slot, one 64-bit load per entry; slot row of
-// record offset `off`: off below 46, off - 36 above (a forward slot is K (10 rows) followed by A, B (30 rows)); rp = row pitch.
+// 128-bit load per pair.  PP: fk = address of this lane's entry of row pair 0 in the ring slot, one 128-bit load per pair of
+// entries (rows are interleaved in pairs, see k_wgpp_block); slot row of record offset `off`: off below 46, off - 36 above
+// (a forward slot is K (10 rows) followed by A, B (30 rows)); rp = bytes per row.
 template <bool PP>
 __device__ __forceinline__ void wgf_ld2(uint32_t fk, int off, uint32_t rp, double &x, double &y)
 {
-    if (PP) {
-        const uint32_t a = fk + (uint32_t)(off < D_AIN ? off : off - 36) * rp;
-        x = wg_ld(a);
-        y = wg_ld(a + rp);
-    } else {
-        wg_ld2(fk + (uint32_t)off * 8u, x, y);
-    }
+    static_assert((D_KIN | D_KC | D_ACLIN | D_ACLC | D_HIN | D_HC | D_EIN | D_EC | D_AIN | D_AC | D_BIN | D_BC) % 2 == 0, "row pairs");
+    if (PP) wg_ld2(fk + (uint32_t)((off < D_AIN ? off : off - 36) >> 1) * (2u * rp), x, y);      // fk: this lane's 16 bytes of row pair 0
+    else wg_ld2(fk + (uint32_t)off * 8u, x, y);
 }
 template <bool PP>
 __device__ __forceinline__ void wgf_ld4(uint32_t fk, int off, uint32_t rp, double (&r)[4])
 {
     wgf_ld2<PP>(fk, off, rp, r[0], r[1]);
     wgf_ld2<PP>(fk, off + 2, rp, r[2], r[3]);
-}
-
-__device__ __forceinline__ void wg_tma(uint32_t dst, const CUtensorMap *map, int col, int row, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 
 // Per-stage hand-over between warps.  The producer warp has written shared memory with all its lanes; __syncwarp orders
@@ -432,7 +417,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                                 for (int e = 0; e < 2; ++e) { in.z[e] = wg_ld(zs + o + 8u * e); in.u[e] = wg_ld(us + o + 8u * e); }
                                 sl = cstep & (WG_PP_R - 1);
                                 if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
-                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 16u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
                             }
@@ -498,7 +483,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                                 o.d[1] = wg_ld(dk + 8);
                                 sl = cstep & (WG_PP_R - 1);
                                 if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
-                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 16u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
                             }
@@ -575,7 +560,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                                 in.u = wg_ld(us + o);
                                 sl = cstep & (WG_PP_R - 1);
                                 if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
-                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 16u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
                             }
@@ -619,7 +604,7 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
                                 in.d2 = wg_ld(ds + (uint32_t)(3 * k + 2) * 8u);
                                 sl = cstep & (WG_PP_R - 1);
                                 if (!pre_ok) wg_wait_spin(rfull + 8u * sl, (cstep / WG_PP_R) & 1u);
-                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 8u;
+                                fk = ring_s + sl * slot_bytes + (uint32_t)lane * 16u;
                             } else {
                                 fk = fac_s + (uint32_t)(k * FW) * 8u;
                             }
@@ -717,63 +702,20 @@ k_admm_iterate_wg(const __grid_constant__ IterParams P, const int TW_arg, const 
             } else if (PP && warp == 4) {
                 // ================= per-problem models: the records of the 2 N sweep stages of this iteration, in the order
                 // the chain warps consume them (backward N-1 .. 0, forward 0 .. N-1), WG_PP_R - 1 stages ahead of them at most
-                const int col0 = tile * TW;
-                (void)col0;
-#ifndef WG_PP_CPASYNC
                 for (int q = 0; q < 2 * N; ++q) {
                     const uint32_t sl = pstep & (WG_PP_R - 1);
                     wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
                     if ((tid & 31) == 0) {
                         const uint32_t dst = ring_s + sl * slot_bytes, bar = rfull + 8u * sl;
-#ifdef WG_PP_TMA_BOXES      // developer build: the slots filled by TMA boxes straight from fac_dec (A/B of DESIGN 4.10)
-                        if (q < N) {
-                            const int k = N - 1 - q;
-                            mbar_expect_tx(bar, (uint32_t)WG_PP_ROWS * rp);
-                            wg_tma(dst, &maps.mB, col0, k * FD, bar);
-                        } else {
-                            const int k = q - N;
-                            mbar_expect_tx(bar, 40u * rp);
-                            wg_tma(dst, &maps.mF0, col0, k * FD, bar);
-                            wg_tma(dst + 10u * rp, &maps.mF1, col0, k * FD + D_AIN, bar);
-                        }
-#else
                         const bool bwd = q < N;
                         const int k = bwd ? N - 1 - q : q - N;
                         const double *src = maps.blk + (((size_t)tile * N + k) * WG_PP_BLK_ROWS + (bwd ? 0 : D_AIN)) * TW;
                         const uint32_t bytes = (bwd ? (uint32_t)WG_PP_ROWS : 40u) * rp;
                         mbar_expect_tx(bar, bytes);
                         bulk_g2s(dst, src, bytes, bar);
-#endif
                     }
                     ++pstep;
                 }
-#else
-                // developer build (-DWG_PP_CPASYNC), measured and dropped: 16-byte cp.async copies by all 32 lanes, completion
-                // reported to the slot's full barrier by every lane (cp.async.mbarrier.arrive.noinc: the barrier counts 32
-                // arrivals) -- 94 us per iteration against 25.9 with the TMA boxes (2,200 cycles per backward stage).
-                constexpr int CPR = PTW > 0 ? PTW / 2 : 1;                         // 16-byte chunks per row of a slot
-                const int ln = tid & 31;
-                for (int q = 0; q < 2 * N; ++q) {
-                    const uint32_t sl = pstep & (WG_PP_R - 1);
-                    wg_wait(rempty + 8u * sl, ((pstep / WG_PP_R) & 1u) ^ 1u);      // both chain warps are done with the slot
-                    const uint32_t dst = ring_s + sl * slot_bytes, bar = rfull + 8u * sl;
-                    const bool bwd = q < N;
-                    const int k = bwd ? N - 1 - q : q - N;
-                    const int nrows = bwd ? WG_PP_ROWS : 40;
-                    const double *src = P.fac_dec + (size_t)(k * FD) * ld;
-#pragma unroll 4
-                    for (int i = ln; i < nrows * CPR; i += 32) {
-                        const int r = i / CPR, c = i - r * CPR;                    // slot row, chunk of the row
-                        const int rr = (bwd || r < 10) ? r : r + 36;               // record row: a forward slot is K, then A, B (rows 46 .. 75)
-                        const int col = col0 + 2 * c;
-                        if ((size_t)col + 2 <= ld)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)r * rp + 16u * c),
-                                         "l"(src + (size_t)rr * ld + col) : "memory");
-                    }
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-                    ++pstep;
-                }
-#endif
             } else if (norms) {
                 // ================= the five norm accumulators, blocks in the oracle's order, behind the prox warps
                 double rr = 0.0, ss = 0.0, xx = 0.0, zz = 0.0, uu = 0.0;
