@@ -387,6 +387,23 @@ def test_per_problem_models_warp_group_horizons(solver, cpu_oracle, P, N, batch,
     assert_bit_identical(got, ref, f"per-problem models, N={N}, batch={batch}")
 
 
+# ---- the same kernel with adaptive rho (no quadratic cost: a rho change rescales u and leaves the factor alone) and with
+# problems leaving the working set between short launches: every repack moves columns, so the tile-blocked copy of the
+# records (k_wgpp_block) is rebuilt for a narrower, ragged working set while rho is still adapting.
+@pytest.mark.parametrize("adapt", [0, 1])
+def test_per_problem_models_warp_group_repacks_and_adaptive_rho(solver, cpu_oracle, P, adapt, kernel_variant):
+    if kernel_variant not in ("auto", "wg"):
+        pytest.skip("the streamed-record warp-group kernel runs when pinned or on narrow working sets")
+    prob, opts = P.cfg4_elliptic(batch=150, N=20, seed=77)
+    opts = dict(opts, max_iter=1500, chunk=7, abstol=1e-4, reltol=1e-4, adapt_rho=adapt, adapt_every=20, adapt_mu=3.0, history=1)
+    got, ref = _both(solver, cpu_oracle, prob, opts)
+    it = ref[3]["iters"]
+    assert it.min() < it.max() and (ref[3]["status"] == 0).mean() > 0.5, "no early exits: test is vacuous"
+    if adapt:
+        assert len(np.unique(ref[3]["rho"])) > 1, "adaptation never fired: test is vacuous"
+    assert_bit_identical(got, ref, f"per-problem models, repacks, adapt={adapt}")
+
+
 # ---- receding-horizon step on the resident batch: admmb_shift_resolve against the oracle's warm-started solve
 @pytest.mark.parametrize("k,from_solution", [(1, True), (1, False), (3, False)])
 def test_shift_resolve_matches_oracle_warm_start(pkg, cpu_oracle, P, k, from_solution, kernel_variant):
