@@ -36,19 +36,4 @@ inline CUtensorMap tmap_rows_f64(const double *base, uint64_t rows, uint64_t ld,
     return m;
 }
 
-// the same array with boxes of [box_rows] x [box_cols] (box_cols * 8 bytes a multiple of 16)
-inline CUtensorMap tmap_box_f64(const double *base, uint64_t rows, uint64_t ld, uint32_t box_rows, uint32_t box_cols)
-{
-    CUtensorMap m;
-    cuuint64_t dims[2] = {ld, rows};
-    cuuint64_t strides[1] = {ld * sizeof(double)};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = tmap_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw CudaFail{cudaErrorInvalidValue, "cuTensorMapEncodeTiled ([rows][ld] FP64 array, custom box) failed"};
-    return m;
-}
-
 }  // namespace admmb
